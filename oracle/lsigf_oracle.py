@@ -1,0 +1,229 @@
+"""CPU oracle for the LSIGF graph-filter path.  TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs may
+import this file.  The product path (`graph-neural-networks_b200/`) never does: it fails loudly when
+the CUDA extension is missing.
+
+What is restated here (citations are /root/reference/alegnn/utils/graphML.py):
+
+* `lsigf_dense`      – `LSIGF(h, S, x, b)`            :83-176  (shift loop :158-161, tap contraction with
+                        flatten order (e,k,g) :170-171, bias :174-175).
+* `lsigf_sparse`     – the same arithmetic with each S_e held as a scipy CSR matrix, so the oracle
+                        scales to N where the reference's dense E x N x N GSO cannot be allocated.
+* `lsigf_grads_*`    – the gradients PyTorch autograd derives for that function.
+* `graph_filter_forward` – `GraphFilter.forward`        :2125-2144 (zero-pad :2131-2135, truncate :2142-2143).
+* `lsigf_dense_torch` – dense torch CPU port used as the *timed* CPU baseline (same op sequence as the
+                        reference: K-1 broadcast batched GEMMs + one contraction GEMM).
+
+Pinning: the reference holds no tests or golden vectors for this path, so the oracle is
+pinned against outputs of the unmodified reference itself, generated in the authoring container by
+`oracle/make_golden.py` and committed under `tests/golden/` (see tests/test_oracle_golden.py), and —
+when /root/reference is present — live against the imported reference (tests/test_oracle_vs_reference.py).
+
+Conventions (reference, graphML.py:104-112): h [F,E,K,G]; S [E,N,N]; x [B,G,N]; b [F,1] or [F,N] or None;
+y [B,F,N].  The shift is the ROW-vector product x·S (graphML.py:159): (x S)[.., j] = sum_i x[.., i] S[i, j].
+All arithmetic here is float64 unless a dtype is passed.
+"""
+import numpy as np
+
+try:  # scipy is only needed by the sparse variants
+    import scipy.sparse as sp
+except Exception:  # pragma: no cover
+    sp = None
+
+
+# --------------------------------------------------------------------------------------------
+# forward
+# --------------------------------------------------------------------------------------------
+def shifted_signals_dense(S, x, K):
+    """z[b,e,k,g,n] = (x_g S_e^k)[n]   — graphML.py:152-161 (k = 0 is x itself for every e)."""
+    S = np.asarray(S)
+    x = np.asarray(x)
+    E, N, _ = S.shape
+    B, G, _ = x.shape
+    z = np.empty((B, E, K, G, N), dtype=np.result_type(S, x))
+    cur = np.broadcast_to(x[:, None, :, :], (B, E, G, N)).copy()
+    z[:, :, 0] = cur
+    for k in range(1, K):
+        # row-vector shift: contract the node index of x with the FIRST node index of S_e
+        cur = np.einsum("begi,eij->begj", cur, S)
+        z[:, :, k] = cur
+    return z
+
+
+def lsigf_dense(h, S, x, b=None):
+    """y[b,f,n] = sum_{e,k,g} h[f,e,k,g] (x_g S_e^k)[n] + bias  — graphML.py:83-176."""
+    h = np.asarray(h)
+    F, E, K, G = h.shape
+    S = np.asarray(S)
+    x = np.asarray(x)
+    assert S.shape[0] == E and S.shape[1] == S.shape[2]
+    assert x.shape[1] == G and x.shape[2] == S.shape[1]
+    z = shifted_signals_dense(S, x, K)
+    y = np.einsum("bekgn,fekg->bfn", z, h)
+    if b is not None:
+        y = y + np.asarray(b)[None, :, :]  # [F,1] or [F,N] broadcast over batch (and nodes)
+    return y
+
+
+def _csr_list(S_list):
+    assert sp is not None, "scipy required for the sparse oracle"
+    return [sp.csr_matrix(S_e) for S_e in S_list]
+
+
+def shifted_signals_sparse(S_list, x, K):
+    """Same as shifted_signals_dense with S_e as scipy sparse matrices (list of length E).
+
+    (x S)[., j] = sum_i x[., i] S[i, j]  ==  (S^T x^T)^T, so with X node-major [N, B*G] the hop is
+    X <- S_e^T X.
+    """
+    S_list = _csr_list(S_list)
+    x = np.asarray(x)
+    B, G, N = x.shape
+    E = len(S_list)
+    X0 = np.ascontiguousarray(x.reshape(B * G, N).T)  # [N, C]
+    z = np.empty((E, K, N, B * G), dtype=X0.dtype)
+    for e in range(E):
+        St = S_list[e].T.tocsr()
+        cur = X0
+        z[e, 0] = cur
+        for k in range(1, K):
+            cur = St @ cur
+            z[e, k] = cur
+    return z  # [E,K,N,C]
+
+
+def lsigf_sparse(h, S_list, x, b=None):
+    """Sparse restatement of LSIGF (graphML.py:83-176); S_list = [S_e as scipy sparse], same semantics."""
+    h = np.asarray(h)
+    F, E, K, G = h.shape
+    x = np.asarray(x)
+    B, _, N = x.shape
+    assert len(S_list) == E and x.shape[1] == G
+    z = shifted_signals_sparse(S_list, x, K).reshape(E, K, N, B, G)
+    y = np.einsum("eknbg,fekg->bfn", z, h)
+    if b is not None:
+        y = y + np.asarray(b)[None, :, :]
+    return y
+
+
+def graph_filter_forward(weight, bias, S, x):
+    """GraphFilter.forward — graphML.py:2125-2144: right-zero-pad the node axis up to N, filter, keep first Nin."""
+    S = np.asarray(S)
+    x = np.asarray(x)
+    N = S.shape[1]
+    B, G, Nin = x.shape
+    if Nin < N:
+        x = np.concatenate([x, np.zeros((B, G, N - Nin), dtype=x.dtype)], axis=2)
+    u = lsigf_dense(weight, S, x, bias)
+    return u[:, :, :Nin]
+
+
+# --------------------------------------------------------------------------------------------
+# backward (what autograd computes for the function above)
+# --------------------------------------------------------------------------------------------
+def lsigf_grads_dense(h, S, x, dy, bias_shape=None):
+    """Returns (dh, dx, db) for upstream gradient dy [B,F,N].
+
+    dh[f,e,k,g] = sum_{b,n} dy[b,f,n] z[b,e,k,g,n]
+    dx          = sum_{e,k} (dy^T-contracted taps) shifted back with S_e^T:  dx_g = sum_{e,k,f} h[f,e,k,g] dy_f (S_e^T)^k
+    db          = sum over batch (and over nodes when the bias is [F,1])
+    """
+    h = np.asarray(h)
+    S = np.asarray(S)
+    x = np.asarray(x)
+    dy = np.asarray(dy)
+    F, E, K, G = h.shape
+    z = shifted_signals_dense(S, x, K)
+    dh = np.einsum("bfn,bekgn->fekg", dy, z)
+    # v[b,e,k,f,n] = (dy_f (S_e^T)^k)[n]
+    St = np.transpose(S, (0, 2, 1))
+    v = shifted_signals_dense(St, dy, K)
+    dx = np.einsum("bekfn,fekg->bgn", v, h)
+    db = None
+    if bias_shape is not None:
+        db = dy.sum(axis=0)
+        if bias_shape[1] == 1:
+            db = db.sum(axis=1, keepdims=True)
+    return dh, dx, db
+
+
+def lsigf_grads_sparse(h, S_list, x, dy, bias_shape=None):
+    h = np.asarray(h)
+    x = np.asarray(x)
+    dy = np.asarray(dy)
+    F, E, K, G = h.shape
+    B, _, N = x.shape
+    S_list = _csr_list(S_list)
+    z = shifted_signals_sparse(S_list, x, K).reshape(E, K, N, B, G)
+    dh = np.einsum("bfn,eknbg->fekg", dy, z)
+    v = shifted_signals_sparse([S_e.T for S_e in S_list], dy, K).reshape(E, K, N, B, F)
+    dx = np.einsum("eknbf,fekg->bgn", v, h)
+    db = None
+    if bias_shape is not None:
+        db = dy.sum(axis=0)
+        if bias_shape[1] == 1:
+            db = db.sum(axis=1, keepdims=True)
+    return dh, dx, db
+
+
+# --------------------------------------------------------------------------------------------
+# dense torch CPU port: the timed CPU baseline (bench.py cpu_baseline / --impl reference)
+# --------------------------------------------------------------------------------------------
+def lsigf_dense_torch(h, S, x, b=None):
+    """Dense torch restatement with the reference's own op mix (graphML.py:152-175): K-1 broadcast
+    batched GEMMs x <- x @ S over a dense E x N x N GSO, the growing stack of shifted signals, one
+    [B,N,EKG] x [EKG,F] contraction GEMM, then the bias add.  Written from the description of that
+    algorithm (SURVEY.md §2.2 a-g), not copied."""
+    import torch
+    F, E, K, G = h.shape
+    B, _, N = x.shape
+    cur = x.unsqueeze(1).expand(B, E, G, N)
+    stack = [cur]
+    Sb = S.unsqueeze(0)
+    for _ in range(1, K):
+        cur = torch.matmul(cur, Sb)  # [B,E,G,N] x [1,E,N,N]
+        stack.append(cur)
+    z = torch.stack(stack, dim=2)  # [B,E,K,G,N]
+    zt = z.permute(0, 4, 1, 2, 3).reshape(B, N, E * K * G)
+    y = torch.matmul(zt, h.reshape(F, E * K * G).t()).permute(0, 2, 1)
+    if b is not None:
+        y = y + b
+    return y
+
+
+# --------------------------------------------------------------------------------------------
+# seeded inputs shared by tests / golden generation
+# --------------------------------------------------------------------------------------------
+def random_sparse_gso(rng, N, avg_deg, E=1, symmetric=False, dtype=np.float64):
+    """E random sparse GSOs as dense [E,N,N] arrays (small N only). Non-symmetric unless asked, so
+    the row-vector convention (x·S vs S·x) is actually exercised."""
+    S = np.zeros((E, N, N), dtype=dtype)
+    p = min(1.0, avg_deg / max(N, 1))
+    for e in range(E):
+        mask = rng.random((N, N)) < p
+        w = rng.standard_normal((N, N))
+        A = np.where(mask, w, 0.0)
+        if symmetric:
+            A = np.triu(A, 1)
+            A = A + A.T
+        # keep the spectral radius near 1 so K hops neither blow up nor vanish
+        scale = np.abs(A).sum(axis=1).max()
+        S[e] = A / (scale if scale > 0 else 1.0)
+    return S
+
+
+def random_case(seed, N, B, G, F, K, E=1, avg_deg=6, bias="F1", symmetric=False):
+    rng = np.random.default_rng(seed)
+    S = random_sparse_gso(rng, N, avg_deg, E, symmetric)
+    x = rng.standard_normal((B, G, N))
+    bound = 1.0 / np.sqrt(G * K)  # graphML.py:2109-2114
+    h = rng.uniform(-bound, bound, (F, E, K, G))
+    if bias == "F1":
+        b = rng.uniform(-bound, bound, (F, 1))
+    elif bias == "FN":
+        b = rng.uniform(-bound, bound, (F, N))
+    else:
+        b = None
+    dy = rng.standard_normal((B, F, N))
+    return dict(h=h, S=S, x=x, b=b, dy=dy)

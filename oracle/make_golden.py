@@ -1,0 +1,139 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (alegnn) in this container.
+
+TEST INFRASTRUCTURE.  Run once here (`python oracle/make_golden.py`); the fixtures are committed because
+/root/reference does not exist on the GPU box.  Every array in a fixture is either a seeded input or an
+output of the reference's own code:
+
+  lsigf_cases.npz   – `alegnn.utils.graphML.LSIGF` (graphML.py:83-176) forward in fp64 and its autograd
+                      gradients (dh, dx, db) for a sweep of shapes (E>1, K in {1,2,3,5}, bias None / Fx1 / FxN,
+                      non-symmetric GSOs), plus the reference's own fp32 forward (its noise floor).
+  graphfilter_cases.npz – `alegnn.utils.graphML.GraphFilter` (graphML.py:2036-2155) incl. the N_in < N
+                      zero-pad / truncate path (:2131-2143).
+  selectiongnn_cfg1.npz – BASELINE.json configs[0]: reference `Graph('SBM',50,...)`, `S = W/lambda_max`,
+                      `SelectionGNN([1,32],[5],...)` (architectures.py:166-180) forward + backward in fp64;
+                      state_dict, input batch, output and the parameter gradients.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_import  # noqa: E402
+import lsigf_oracle as orc  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+# (seed, N, B, G, F, K, E, avg_deg, bias, symmetric)
+LSIGF_CASES = [
+    (101, 12, 2, 3, 4, 3, 1, 4, "F1", False),
+    (102, 17, 3, 2, 5, 5, 2, 5, "FN", False),
+    (103, 9, 1, 1, 6, 1, 1, 3, "F1", False),     # K = 1: no hops
+    (104, 20, 4, 4, 4, 2, 3, 6, None, False),
+    (105, 33, 2, 8, 8, 5, 1, 8, "F1", True),
+    (106, 50, 5, 1, 32, 5, 1, 10, "F1", True),   # cfg1-shaped layer
+    (107, 64, 2, 16, 12, 4, 2, 7, "FN", False),
+    (108, 41, 3, 5, 7, 3, 1, 41, "F1", False),   # fully dense GSO
+]
+
+GF_CASES = [
+    # (seed, N, Nin, B, G, F, K, E, bias)
+    (201, 24, 24, 3, 2, 4, 3, 1, True),
+    (202, 24, 15, 2, 3, 5, 4, 2, True),          # zero-pad + truncate
+    (203, 30, 7, 4, 1, 3, 2, 1, False),
+]
+
+
+def gen_lsigf(gml):
+    out = {}
+    for (seed, N, B, G, F, K, E, deg, bias, sym) in LSIGF_CASES:
+        c = orc.random_case(seed, N, B, G, F, K, E, deg, bias, sym)
+        h = torch.tensor(c["h"], dtype=torch.float64, requires_grad=True)
+        x = torch.tensor(c["x"], dtype=torch.float64, requires_grad=True)
+        S = torch.tensor(c["S"], dtype=torch.float64)
+        b = None if c["b"] is None else torch.tensor(c["b"], dtype=torch.float64, requires_grad=True)
+        y = gml.LSIGF(h, S, x, b)
+        dy = torch.tensor(c["dy"], dtype=torch.float64)
+        y.backward(dy)
+        y32 = gml.LSIGF(h.detach().float(), S.float(), x.detach().float(),
+                        None if b is None else b.detach().float())
+        key = "c%d" % seed
+        out[key + "_meta"] = np.array([seed, N, B, G, F, K, E, deg, {"F1": 1, "FN": 2, None: 0}[bias], int(sym)])
+        for name, val in (("h", c["h"]), ("S", c["S"]), ("x", c["x"]), ("dy", c["dy"])):
+            out[key + "_" + name] = val
+        if c["b"] is not None:
+            out[key + "_b"] = c["b"]
+            out[key + "_db"] = b.grad.numpy()
+        out[key + "_y"] = y.detach().numpy()
+        out[key + "_y32"] = y32.numpy()
+        out[key + "_dh"] = h.grad.numpy()
+        out[key + "_dx"] = x.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "lsigf_cases.npz"), **out)
+    print("lsigf_cases.npz:", len(LSIGF_CASES), "cases")
+
+
+def gen_graphfilter(gml):
+    out = {}
+    for (seed, N, Nin, B, G, F, K, E, bias) in GF_CASES:
+        rng = np.random.default_rng(seed)
+        S = orc.random_sparse_gso(rng, N, 5, E)
+        x = rng.standard_normal((B, G, Nin))
+        torch.manual_seed(seed)
+        layer = gml.GraphFilter(G, F, K, E, bias).double()
+        layer.addGSO(torch.tensor(S))
+        xt = torch.tensor(x, requires_grad=True)
+        y = layer(xt)
+        dy = rng.standard_normal(tuple(y.shape))
+        y.backward(torch.tensor(dy))
+        key = "g%d" % seed
+        out[key + "_meta"] = np.array([seed, N, Nin, B, G, F, K, E, int(bias)])
+        out[key + "_S"] = S
+        out[key + "_x"] = x
+        out[key + "_dy"] = dy
+        out[key + "_weight"] = layer.weight.detach().numpy()
+        out[key + "_dweight"] = layer.weight.grad.numpy()
+        if bias:
+            out[key + "_bias"] = layer.bias.detach().numpy()
+            out[key + "_dbias"] = layer.bias.grad.numpy()
+        out[key + "_y"] = y.detach().numpy()
+        out[key + "_dx"] = xt.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "graphfilter_cases.npz"), **out)
+    print("graphfilter_cases.npz:", len(GF_CASES), "cases")
+
+
+def gen_selectiongnn_cfg1(gml):
+    import torch.nn as nn
+    import alegnn.utils.graphTools as graphTools
+    import alegnn.modules.architectures as archit
+    np.random.seed(0)
+    torch.manual_seed(0)
+    torch.set_default_dtype(torch.float64)
+    try:
+        G = graphTools.Graph("SBM", 50, {"nCommunities": 5, "probIntra": 0.8, "probInter": 0.2})
+        G.computeGFT()
+        S = G.W / np.max(np.real(G.E))  # examples/sourceLocGNN.py:752
+        net = archit.SelectionGNN([1, 32], [5], True, nn.ReLU, [50], gml.NoPool, [1], [5], S)
+        x = np.random.randn(20, 1, 50)
+        xt = torch.tensor(x, requires_grad=True)
+        y = net(xt)
+        dy = np.random.randn(*y.shape)
+        y.backward(torch.tensor(dy))
+        out = {"S": S, "x": x, "dy": dy, "y": y.detach().numpy(), "dx": xt.grad.numpy()}
+        for k, v in net.state_dict().items():
+            out["sd_" + k] = v.numpy()
+        for k, p in net.named_parameters():
+            out["grad_" + k] = p.grad.numpy()
+    finally:
+        torch.set_default_dtype(torch.float32)
+    np.savez_compressed(os.path.join(OUT, "selectiongnn_cfg1.npz"), **out)
+    print("selectiongnn_cfg1.npz: keys", sorted(out.keys()))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    gml = ref_import.import_reference()
+    gen_lsigf(gml)
+    gen_graphfilter(gml)
+    gen_selectiongnn_cfg1(gml)
