@@ -1,0 +1,10 @@
+"""b200gf — B200-native LSIGF graph-filter path (drop-in for alegnn.utils.graphML.LSIGF / GraphFilter).
+
+The directory is called `graph-neural-networks_b200` (not a valid Python identifier); import it through the
+`gnn_b200` loader module at the repo root:  `import gnn_b200 as b200`.
+"""
+from . import _cabi  # noqa: F401
+from .gso import SparseGSO, Plan, plan_for, clear_plan_cache  # noqa: F401
+from .graphML import LSIGF, GraphFilter, install, uninstall, to_node_major, node_major_ld, padded_ld  # noqa: F401
+
+__all__ = ["LSIGF", "GraphFilter", "SparseGSO", "Plan", "plan_for", "install", "uninstall"]

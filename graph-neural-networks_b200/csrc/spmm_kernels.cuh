@@ -1,0 +1,184 @@
+// Kernels of the graph shift ("hop"); included by spmm.cu (the library) and tools/spmm_sweep.cu (tuning sweeps).
+//
+//   dst[r, :] = sum_j A[r, j] * src[j, :]        A = CSR gather operator, src/dst node-major [rows, ld]
+//
+// Mapping (sm_100a, 148 SMs):
+//   * one warp per (row, column chunk) work item, grid-stride over items in chunk-major order, so that at any
+//     time all resident warps gather from the same column slab (keeps it L2-resident when N * chunk_bytes fits);
+//   * L lanes x 16-byte vectors cover the chunk; the 32/L lane groups each take a different neighbour, so one
+//     warp-wide LDG.128 fetches 32/L whole neighbour rows (every 32-byte sector fully used);
+//   * U independent LDG.128 per lane are in flight before the FMAs (memory-level parallelism);
+//   * col/val of a row are read once, coalesced (lane i holds entry i), and broadcast with SHFL;
+//   * the next row's col/val and the rowptr pair of the row after that are prefetched while the current row is
+//     being gathered (PF).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200gf {
+
+template <typename T, int VEC>
+struct Acc {
+  T v[VEC];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) v[i] = T(0);
+  }
+};
+
+__device__ __forceinline__ uint64_t evict_last_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
+// HINT 0: ld.global.nc (default policy)   1: + L1::no_allocate (gathered rows have no L1 reuse)
+// HINT 2: L1::no_allocate + L2::evict_last on the gathered rows (fight for L2 residency of the feature slab)
+template <typename T, int VEC, int HINT>
+__device__ __forceinline__ Acc<T, VEC> load_vec(const T* p) {
+  Acc<T, VEC> a;
+  if constexpr (VEC == 4) {
+    float4 t;
+    if constexpr (HINT == 0) {
+      t = __ldg(reinterpret_cast<const float4*>(p));
+    } else if constexpr (HINT == 1) {
+      asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "l"(p));
+    } else {
+      asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                   : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "l"(p), "l"(evict_last_policy()));
+    }
+    a.v[0] = t.x; a.v[1] = t.y; a.v[2] = t.z; a.v[3] = t.w;
+  } else if constexpr (VEC == 2) {
+    double2 t;
+    if constexpr (HINT == 0) {
+      t = __ldg(reinterpret_cast<const double2*>(p));
+    } else if constexpr (HINT == 1) {
+      asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(t.x), "=d"(t.y) : "l"(p));
+    } else {
+      asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
+                   : "=d"(t.x), "=d"(t.y) : "l"(p), "l"(evict_last_policy()));
+    }
+    a.v[0] = t.x; a.v[1] = t.y;
+  } else {
+    a.v[0] = __ldg(p);
+  }
+  return a;
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ void store_vec(T* p, const Acc<T, VEC>& a) {
+  if constexpr (VEC == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+  } else if constexpr (VEC == 2) {
+    *reinterpret_cast<double2*>(p) = make_double2(a.v[0], a.v[1]);
+  } else {
+    p[0] = a.v[0];
+  }
+}
+
+// streaming reads of the CSR arrays (each entry is used once per hop)
+template <typename V>
+__device__ __forceinline__ V ld_stream(const V* p) { return __ldcs(p); }
+
+constexpr unsigned FULL = 0xffffffffu;
+
+template <typename T, int VEC, int L, int U, int THREADS, int MINB, int HINT, bool PF>
+__global__ void __launch_bounds__(THREADS, MINB)
+spmm_hop_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                const T* __restrict__ val, const T* __restrict__ src, int64_t src_ld,
+                T* __restrict__ dst, int64_t dst_ld, int64_t n_rows, int C, int n_chunks) {
+  constexpr int S = 32 / L;  // neighbours gathered concurrently by one warp
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / L;
+  const int cl = lane % L;
+  const int64_t n_warps = (int64_t)gridDim.x * (THREADS >> 5);
+  const int64_t n_items = n_rows * n_chunks;
+  int64_t item = (int64_t)blockIdx.x * (THREADS >> 5) + (threadIdx.x >> 5);
+  if (item >= n_items) return;
+
+  // software pipeline state: current row (beg, end, c, v), next row (nbeg, nend)
+  int64_t row = item % n_rows;
+  int64_t beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+  int32_t c = 0;
+  T v = T(0);
+  if (beg + lane < end) { c = ld_stream(col + beg + lane); v = ld_stream(val + beg + lane); }
+  int64_t nbeg = 0, nend = 0;
+  if (PF && item + n_warps < n_items) {
+    const int64_t nrow = (item + n_warps) % n_rows;
+    nbeg = __ldg(rowptr + nrow); nend = __ldg(rowptr + nrow + 1);
+  }
+
+  while (true) {
+    const int chunk = (int)(item / n_rows);
+    row = item - (int64_t)chunk * n_rows;
+    const int cbase = chunk * (L * VEC) + cl * VEC;
+    const bool col_ok = cbase < C;
+    const T* __restrict__ srcc = src + cbase;
+
+    // prefetch: next row's first 32 (col, val), and the rowptr pair of the row after that
+    const int64_t next = item + n_warps;
+    const bool has_next = next < n_items;
+    int32_t nc = 0;
+    T nv = T(0);
+    int64_t nnbeg = 0, nnend = 0;
+    if (PF) {
+      if (has_next && nbeg + lane < nend) { nc = ld_stream(col + nbeg + lane); nv = ld_stream(val + nbeg + lane); }
+      if (next + n_warps < n_items) {
+        const int64_t nnrow = (next + n_warps) % n_rows;
+        nnbeg = __ldg(rowptr + nnrow); nnend = __ldg(rowptr + nnrow + 1);
+      }
+    }
+
+    Acc<T, VEC> acc;
+    acc.zero();
+    for (int64_t base = beg; base < end; base += 32) {
+      if (base != beg) {  // rows longer than 32: fetch the following entries (not prefetched)
+        c = 0; v = T(0);
+        if (base + lane < end) { c = ld_stream(col + base + lane); v = ld_stream(val + base + lane); }
+      }
+      const int cnt = (int)((end - base) < 32 ? (end - base) : 32);
+#pragma unroll 1
+      for (int j = 0; j < cnt; j += S * U) {
+        Acc<T, VEC> buf[U];
+        T w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int jj = j + u * S + sub;
+          const int32_t cc = __shfl_sync(FULL, c, jj & 31);
+          const T ww = __shfl_sync(FULL, v, jj & 31);
+          const bool ok = (jj < cnt) && col_ok;
+          w[u] = ok ? ww : T(0);
+          if (ok) buf[u] = load_vec<T, VEC, HINT>(srcc + (int64_t)cc * src_ld);
+          else buf[u].zero();
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc.v[i] = fma(w[u], buf[u].v[i], acc.v[i]);
+        }
+      }
+    }
+    // fold the S neighbour groups together
+#pragma unroll
+    for (int off = L; off < 32; off <<= 1) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc.v[i] += __shfl_xor_sync(FULL, acc.v[i], off);
+    }
+    if (sub == 0 && col_ok) store_vec<T, VEC>(dst + row * dst_ld + cbase, acc);
+
+    if (!has_next) break;
+    item = next;
+    if (PF) {
+      beg = nbeg; end = nend; c = nc; v = nv;
+      nbeg = nnbeg; nend = nnend;
+    } else {
+      row = item % n_rows;
+      beg = __ldg(rowptr + row); end = __ldg(rowptr + row + 1);
+      c = 0; v = T(0);
+      if (beg + lane < end) { c = ld_stream(col + beg + lane); v = ld_stream(val + beg + lane); }
+    }
+  }
+}
+
+}  // namespace b200gf

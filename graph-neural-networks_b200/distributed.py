@@ -1,0 +1,223 @@
+"""Multi-GPU LSIGF (one process per GPU, torch.distributed over NCCL / NVLink 5) — SURVEY.md §8e.
+
+Two shardings of  y = sum_{e,k} (x S_e^k) h_{e,k} + b :
+
+  mode="nodes"     1-D node partition.  Rank p owns rows [r_p, r_{p+1}) of every node-major matrix and the matching
+                   rows of the gather operators (global column indices).  Each of the K-1 hops is followed by an
+                   NCCL all-gather of the freshly computed rows (the halo of an Erdős–Rényi graph is ~all remote
+                   nodes, so the "boundary rows" are the whole block); the tap contraction and the bias are
+                   row-local.  This is the sharding BASELINE.json names.
+  mode="features"  The graph is replicated and the B*G feature columns are split: a hop never mixes columns, so the
+                   K-1 hops need NO communication and each rank's gathered slab (N x C/P) shrinks towards the L2.
+                   One reduce-scatter of the partial [N, B*F] outputs (the g-sum of the contraction is split across
+                   ranks) ends the call.  The right choice whenever S fits on each GPU (SURVEY §8e "column split").
+
+The arithmetic goes through `ops` (the C-ABI building blocks b200gf_hop / b200gf_tap_contract on CUDA).  The
+world_size-2 gloo tests inject an oracle-backed `ops` to exercise the partitioning / collective choreography on CPU;
+the product default has no CPU path.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _cabi
+from .gso import Plan, SparseGSO
+
+_ENUM = {torch.float32: _cabi.F32, torch.float64: _cabi.F64}
+
+
+def _pad_ld(C, dtype):
+    q = 8 if dtype == torch.float32 else 4
+    return (C + q - 1) // q * q
+
+
+def row_slice(csr, r0, r1):
+    """rows [r0, r1) of a host CSR (rowptr, col, val); rows beyond the matrix are empty (zero padding)."""
+    rowptr, col, val = csr
+    n = len(rowptr) - 1
+    rp = rowptr[np.minimum(np.arange(r0, r1 + 1), n)]
+    lo, hi = int(rp[0]), int(rp[-1])
+    return (rp - lo).astype(np.int64), col[lo:hi], val[lo:hi]
+
+
+def transpose_csr(csr, N):
+    import scipy.sparse as sp
+    rowptr, col, val = csr
+    m = sp.csr_matrix((val, col, rowptr), shape=(N, N)).T.tocsr()
+    m.sort_indices()
+    return m.indptr.astype(np.int64), m.indices.astype(np.int32), m.data
+
+
+class CudaOps:
+    """Building blocks on the GPU through the C ABI (include/b200gf.h)."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.lib = _cabi.load()
+
+    def make_plan_ops(self, fwd, bwd, n_rows, n_cols, dtype):
+        return Plan.from_ops(fwd, bwd, n_rows, n_cols, dtype, self.device)
+
+    def make_plan_full(self, gso):
+        return gso.plan(self.device)
+
+    def _st(self):
+        return torch.cuda.current_stream().cuda_stream
+
+    def hop(self, plan, e, direction, src, dst, C):
+        _cabi.check(self.lib.b200gf_hop(plan.handle, e, direction, src.data_ptr(), src.stride(0), dst.data_ptr(),
+                                        dst.stride(0), C, self._st()))
+
+    def pack_taps(self, h, transpose):
+        F, E, K, G = h.shape
+        T = 1 + E * (K - 1)
+        W = torch.empty((T, F, G) if transpose else (T, G, F), dtype=h.dtype, device=h.device)
+        _cabi.check(self.lib.b200gf_pack_taps(_ENUM[h.dtype], h.contiguous().data_ptr(), W.data_ptr(), F, E, K, G,
+                                              1 if transpose else 0, self._st()))
+        return W
+
+    def tap_contract(self, zs, W, bias, out, n_rows, B, P, Q, bias_per_node=0):
+        T = len(zs)
+        _cabi.check(self.lib.b200gf_tap_contract(
+            _ENUM[out.dtype], n_rows, B, P, Q, T, _cabi.ptr_array([z.data_ptr() for z in zs]),
+            _cabi.i64_array([z.stride(0) for z in zs]), W.data_ptr(), None if bias is None else bias.data_ptr(),
+            bias_per_node, out.data_ptr(), out.stride(0), 0, self._st()))
+
+
+class PartitionedLSIGF:
+    """LSIGF forward sharded over the ranks of `group` (see module docstring).
+
+    nodes mode:     forward(h, x_rows, b)  x_rows  node-major [rows_per_rank, B*G]  -> y_rows [rows_per_rank, B*F]
+    features mode:  forward(h, x_cols, b)  x_cols  node-major [N, B*(G/P)]          -> y_rows [rows_per_rank, B*F]
+    In both, row block p covers global nodes [p*rows_per_rank, (p+1)*rows_per_rank) (the last block is zero-padded).
+    """
+
+    def __init__(self, gso, mode="nodes", group=None, device=None, ops=None):
+        assert mode in ("nodes", "features")
+        self.mode = mode
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.N, self.E, self.dtype = gso.N, gso.E, gso.dtype
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.ops = ops if ops is not None else CudaOps(self.device)
+        P = self.world
+        self.rows_per_rank = (self.N + P - 1) // P
+        self.n_pad = self.rows_per_rank * P
+        self.r0 = self.rank * self.rows_per_rank
+        self.r1 = self.r0 + self.rows_per_rank
+        if mode == "nodes":
+            fwd, bwd = [], []
+            for e in range(self.E):
+                st = transpose_csr(gso.csr[e], self.N)
+                fwd.append(row_slice(st, self.r0, self.r1))
+                bwd.append(row_slice(gso.csr[e], self.r0, self.r1))
+            self.local_nnz = int(sum(f[0][-1] for f in fwd))
+            self.plan = self.ops.make_plan_ops(fwd, bwd, self.rows_per_rank, self.n_pad, self.dtype)
+        else:
+            self.local_nnz = gso.nnz()
+            self.plan = self.ops.make_plan_full(gso)
+        self._bufs = {}
+
+    # -- helpers -----------------------------------------------------------------------------------
+    def feature_slice(self, G):
+        """[g0, g1) of the in-features this rank owns in features mode."""
+        per = (G + self.world - 1) // self.world
+        g0 = min(G, self.rank * per)
+        return g0, min(G, g0 + per)
+
+    def _buffers(self, key, shape):
+        b = self._bufs.get(key)
+        if b is None or tuple(b.shape) != tuple(shape):
+            b = torch.zeros(shape, dtype=self.dtype, device=self.device)
+            self._bufs[key] = b
+        return b
+
+    # -- forward -----------------------------------------------------------------------------------
+    def forward(self, h, x_local, b=None, B=1):
+        """B (batch size) is only read in features mode, where it cannot be inferred from an empty column slice."""
+        if self.mode == "nodes":
+            return self._forward_nodes(h, x_local, b)
+        return self._forward_features(h, x_local, b, B)
+
+    def _forward_nodes(self, h, x_rows, b):
+        F, E, K, G = h.shape
+        C = x_rows.shape[1]
+        B = C // G
+        assert E == self.E and C == B * G and x_rows.shape[0] == self.rows_per_rank
+        ld = _pad_ld(C, self.dtype)
+        R = self.rows_per_rank
+        W = self.ops.pack_taps(h, False)
+        # full-height sources for every hop that has a successor; the last hop of each e only needs local rows
+        full0 = self._buffers(("z0", C), (self.n_pad, ld))
+        full0[self.r0:self.r1, :C].copy_(x_rows)
+        dist.all_gather_into_tensor(full0.view(-1), full0[self.r0:self.r1].reshape(-1), group=self.group)
+        zs = [full0[self.r0:self.r1]]
+        for e in range(E):
+            src = full0
+            for k in range(1, K):
+                last = k == K - 1
+                if last:
+                    dst_rows = self._buffers(("zl", e, C), (R, ld))
+                    self.ops.hop(self.plan, e, _cabi.HOP_FWD, src, dst_rows, C)
+                else:
+                    full = self._buffers(("z", e, k, C), (self.n_pad, ld))
+                    dst_rows = full[self.r0:self.r1]
+                    self.ops.hop(self.plan, e, _cabi.HOP_FWD, src, dst_rows, C)
+                    dist.all_gather_into_tensor(full.view(-1), dst_rows.reshape(-1), group=self.group)
+                    src = full
+                zs.append(dst_rows)
+        y = torch.empty((R, _pad_ld(B * F, self.dtype)), dtype=self.dtype, device=self.device)
+        bias = None
+        if b is not None:
+            assert b.shape[1] == 1, "per-node bias is not supported by the partitioned path"
+            bias = b.contiguous()
+        self.ops.tap_contract(zs, W, bias, y, R, B, G, F)
+        return y[:, :B * F]
+
+    def _forward_features(self, h, x_cols, b, B):
+        F, E, K, G = h.shape
+        g0, g1 = self.feature_slice(G)
+        Gl = g1 - g0
+        R = self.rows_per_rank
+        Cl = B * Gl
+        ldf = _pad_ld(B * F, self.dtype)
+        part = self._buffers(("part", B, F), (self.n_pad, ldf))
+        if Gl > 0:
+            assert x_cols.shape[0] == self.N and x_cols.shape[1] == Cl
+            ld = _pad_ld(Cl, self.dtype)
+            z0 = self._buffers(("fz0", Cl), (self.N, ld))
+            z0[:, :Cl].copy_(x_cols)
+            zs = [z0]
+            for e in range(E):
+                src = z0
+                for k in range(1, K):
+                    dst = self._buffers(("fz", e, k, Cl), (self.N, ld))
+                    self.ops.hop(self.plan, e, _cabi.HOP_FWD, src, dst, Cl)
+                    zs.append(dst)
+                    src = dst
+            W = self.ops.pack_taps(h[:, :, :, g0:g1].contiguous(), False)
+            self.ops.tap_contract(zs, W, None, part[:self.N], self.N, B, Gl, F)
+        else:
+            part.zero_()
+        y = torch.empty((R, ldf), dtype=self.dtype, device=self.device)
+        reduce_scatter_rows(y, part, self.group)
+        y = y[:, :B * F]
+        if b is not None:
+            assert b.shape[1] == 1
+            y = y.view(R, B, F) + b.view(1, 1, F)
+            y = y.reshape(R, B * F)
+        return y
+
+
+def reduce_scatter_rows(out_rows, full, group=None):
+    """out_rows[rank block] = sum over ranks of full[rank block]; NCCL reduce-scatter (gloo: all-reduce + slice)."""
+    backend = dist.get_backend(group)
+    if backend == "nccl":
+        dist.reduce_scatter_tensor(out_rows.view(-1), full.view(-1), op=dist.ReduceOp.SUM, group=group)
+    else:
+        tmp = full.clone()
+        dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=group)
+        r = dist.get_rank(group)
+        R = out_rows.shape[0]
+        out_rows.copy_(tmp[r * R:(r + 1) * R])

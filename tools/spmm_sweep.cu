@@ -1,0 +1,156 @@
+// Tuning sweep for the hop kernel (spmm_kernels.cuh) on a synthetic random graph.  Not part of the library.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 tools/spmm_sweep.cu -o tools/spmm_sweep
+//   tools/spmm_sweep [N=1000000] [deg=32] [C=64] [reps=10] [peakGBs=6566.7]
+// Prints one line per variant: registers, resident blocks/SM, ms per hop, algorithmic GB/s (gather model,
+// SURVEY.md §8d) and the fraction of the measured HBM copy bandwidth.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <vector>
+
+#include "../graph-neural-networks_b200/csrc/spmm_kernels.cuh"
+
+using namespace b200gf;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1);} } while (0)
+
+struct Problem {
+  int64_t N; int C; int64_t nnz;
+  int64_t* rowptr; int32_t* col; float* val; float* src; float* dst; float* ref;
+  int sm_count;
+  double bytes;
+};
+
+template <int L, int U, int THREADS, int MINB, int HINT, bool PF>
+void run(const Problem& P, const char* name, int reps, double peak, int blocks_per_sm_override = 0, bool is_ref = false) {
+  auto kern = spmm_hop_kernel<float, 4, L, U, THREADS, MINB, HINT, PF>;
+  cudaFuncAttributes fa;
+  CK(cudaFuncGetAttributes(&fa, kern));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, 0));
+  int use = blocks_per_sm_override > 0 ? std::min(blocks_per_sm_override, occ) : occ;
+  const int n_chunks = (P.C + L * 4 - 1) / (L * 4);
+  const int64_t items = P.N * n_chunks;
+  int64_t blocks = std::min<int64_t>((items + THREADS / 32 - 1) / (THREADS / 32), (int64_t)P.sm_count * use);
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaMemset(P.dst, 0xff, (size_t)P.N * P.C * 4));
+  for (int i = 0; i < 2; ++i)
+    kern<<<(unsigned)blocks, THREADS>>>(P.rowptr, P.col, P.val, P.src, P.C, P.dst, P.C, P.N, P.C, n_chunks);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  float best = 1e30f, sum = 0;
+  for (int i = 0; i < reps; ++i) {
+    CK(cudaEventRecord(e0));
+    kern<<<(unsigned)blocks, THREADS>>>(P.rowptr, P.col, P.val, P.src, P.C, P.dst, P.C, P.N, P.C, n_chunks);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    best = std::min(best, ms); sum += ms;
+  }
+  // correctness vs the first variant
+  double maxdiff = 0;
+  if (is_ref) {
+    CK(cudaMemcpy(P.ref, P.dst, (size_t)P.N * P.C * 4, cudaMemcpyDeviceToDevice));
+  } else {
+    std::vector<float> a(1 << 16), b(1 << 16);
+    CK(cudaMemcpy(a.data(), P.dst, a.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(b.data(), P.ref, b.size() * 4, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < a.size(); ++i) maxdiff = std::max(maxdiff, (double)fabsf(a[i] - b[i]));
+  }
+  const double avg = sum / reps;
+  printf("%-34s regs=%3d occ=%2d use=%2d blocks=%6lld  avg %.3f ms  best %.3f ms  %.0f GB/s  frac %.3f  maxdiff %.2e\n",
+         name, fa.numRegs, occ, use, (long long)blocks, avg, best, P.bytes / (avg * 1e-3) / 1e9,
+         P.bytes / (avg * 1e-3) / 1e9 / peak, maxdiff);
+  fflush(stdout);
+}
+
+int main(int argc, char** argv) {
+  const int64_t N = argc > 1 ? atoll(argv[1]) : 1000000;
+  const int deg = argc > 2 ? atoi(argv[2]) : 32;
+  const int C = argc > 3 ? atoi(argv[3]) : 64;
+  const int reps = argc > 4 ? atoi(argv[4]) : 10;
+  const double peak = argc > 5 ? atof(argv[5]) : 6566.7;
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
+  printf("device %s  SMs %d  N=%lld deg=%d C=%d\n", prop.name, prop.multiProcessorCount, (long long)N, deg, C);
+
+  std::mt19937_64 rng(12345);
+  std::poisson_distribution<int> pd(deg);
+  std::vector<int64_t> rowptr(N + 1, 0);
+  for (int64_t i = 0; i < N; ++i) rowptr[i + 1] = rowptr[i] + pd(rng);
+  const int64_t nnz = rowptr[N];
+  std::vector<int32_t> col(nnz);
+  std::vector<float> val(nnz);
+  std::uniform_int_distribution<int32_t> ud(0, (int32_t)N - 1);
+  for (int64_t i = 0; i < N; ++i) {
+    for (int64_t j = rowptr[i]; j < rowptr[i + 1]; ++j) col[j] = ud(rng);
+    std::sort(col.begin() + rowptr[i], col.begin() + rowptr[i + 1]);
+  }
+  for (int64_t j = 0; j < nnz; ++j) val[j] = 1.0f / deg;
+  std::vector<float> x((size_t)N * C);
+  for (auto& v : x) v = (float)((rng() >> 40) * (1.0 / (1 << 24))) - 0.5f;
+
+  Problem P;
+  P.N = N; P.C = C; P.nnz = nnz; P.sm_count = prop.multiProcessorCount;
+  CK(cudaMalloc(&P.rowptr, (N + 1) * 8)); CK(cudaMalloc(&P.col, nnz * 4)); CK(cudaMalloc(&P.val, nnz * 4));
+  CK(cudaMalloc(&P.src, (size_t)N * C * 4)); CK(cudaMalloc(&P.dst, (size_t)N * C * 4)); CK(cudaMalloc(&P.ref, (size_t)N * C * 4));
+  CK(cudaMemcpy(P.rowptr, rowptr.data(), (N + 1) * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(P.col, col.data(), nnz * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(P.val, val.data(), nnz * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(P.src, x.data(), (size_t)N * C * 4, cudaMemcpyHostToDevice));
+  P.bytes = (double)nnz * 8 + (double)(N + 1) * 8 + (double)nnz * C * 4 + (double)N * C * 4;
+  printf("nnz=%lld  algorithmic bytes/hop %.3f GB  (at %.0f GB/s: %.3f ms)\n", (long long)nnz, P.bytes / 1e9, peak,
+         P.bytes / peak / 1e6);
+
+  // copy-bandwidth sanity line (same definition as MEASURED_PEAKS.json: read + write bytes)
+  {
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const size_t nb = (size_t)N * C * 4;
+    CK(cudaMemcpy(P.dst, P.src, nb, cudaMemcpyDeviceToDevice));
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < 10; ++i) CK(cudaMemcpyAsync(P.dst, P.src, nb, cudaMemcpyDeviceToDevice));
+    CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    printf("cudaMemcpy D2D %zu MB: %.0f GB/s (read+write)\n", nb >> 20, 2.0 * nb * 10 / (ms * 1e-3) / 1e9);
+  }
+
+  //   L   U  THR MINB HINT PF
+  if (C <= 64) {
+    run<16, 4, 256, 1, 1, true>(P, "L16 U4 t256 mb1 noalloc PF", reps, peak, 0, true);
+    run<16, 4, 256, 1, 0, true>(P, "L16 U4 t256 mb1 ldg PF", reps, peak);
+    run<16, 4, 256, 1, 2, true>(P, "L16 U4 t256 mb1 evict_last PF", reps, peak);
+    run<16, 4, 256, 1, 1, false>(P, "L16 U4 t256 mb1 noalloc noPF", reps, peak);
+    run<16, 2, 256, 1, 1, true>(P, "L16 U2 t256 mb1 noalloc PF", reps, peak);
+    run<16, 8, 256, 1, 1, true>(P, "L16 U8 t256 mb1 noalloc PF", reps, peak);
+    run<16, 4, 256, 5, 1, true>(P, "L16 U4 t256 mb5 noalloc PF", reps, peak);
+    run<16, 4, 256, 6, 1, true>(P, "L16 U4 t256 mb6 noalloc PF", reps, peak);
+    run<16, 4, 256, 8, 1, true>(P, "L16 U4 t256 mb8 noalloc PF", reps, peak);
+    run<16, 2, 256, 8, 1, true>(P, "L16 U2 t256 mb8 noalloc PF", reps, peak);
+    run<16, 8, 256, 4, 1, true>(P, "L16 U8 t256 mb4 noalloc PF", reps, peak);
+    run<16, 8, 256, 3, 1, true>(P, "L16 U8 t256 mb3 noalloc PF", reps, peak);
+    run<16, 4, 128, 1, 1, true>(P, "L16 U4 t128 mb1 noalloc PF", reps, peak);
+    run<16, 4, 512, 1, 1, true>(P, "L16 U4 t512 mb1 noalloc PF", reps, peak);
+    run<16, 4, 1024, 1, 1, true>(P, "L16 U4 t1024 mb1 noalloc PF", reps, peak);
+    // occupancy sensitivity at fixed code: cap resident blocks per SM
+    run<16, 4, 256, 1, 1, true>(P, "L16 U4 t256 mb1 noalloc PF cap2", reps, peak, 2);
+    run<16, 4, 256, 1, 1, true>(P, "L16 U4 t256 mb1 noalloc PF cap3", reps, peak, 3);
+    // column split: two passes over 32-column halves / four over 16-column quarters (L2 residency experiment)
+    run<8, 4, 256, 1, 1, true>(P, "L8  U4 (2 x 32-col passes)", reps, peak);
+    run<8, 8, 256, 1, 1, true>(P, "L8  U8 (2 x 32-col passes)", reps, peak);
+    run<4, 8, 256, 1, 1, true>(P, "L4  U8 (4 x 16-col passes)", reps, peak);
+    run<4, 8, 256, 1, 2, true>(P, "L4  U8 (4 x 16-col) evict_last", reps, peak);
+  } else {
+    run<32, 4, 256, 1, 1, true>(P, "L32 U4 t256 mb1 noalloc PF", reps, peak, 0, true);
+    run<32, 4, 256, 1, 0, true>(P, "L32 U4 t256 mb1 ldg PF", reps, peak);
+    run<32, 4, 256, 1, 2, true>(P, "L32 U4 t256 mb1 evict_last PF", reps, peak);
+    run<32, 8, 256, 1, 1, true>(P, "L32 U8 t256 mb1 noalloc PF", reps, peak);
+    run<32, 2, 256, 1, 1, true>(P, "L32 U2 t256 mb1 noalloc PF", reps, peak);
+    run<32, 4, 256, 6, 1, true>(P, "L32 U4 t256 mb6 noalloc PF", reps, peak);
+    run<32, 8, 256, 4, 1, true>(P, "L32 U8 t256 mb4 noalloc PF", reps, peak);
+    run<32, 4, 512, 1, 1, true>(P, "L32 U4 t512 mb1 noalloc PF", reps, peak);
+    run<16, 4, 256, 1, 1, true>(P, "L16 U4 (64-col chunks)", reps, peak);
+    run<8, 8, 256, 1, 1, true>(P, "L8 U8 (32-col chunks)", reps, peak);
+  }
+  return 0;
+}
