@@ -17,13 +17,15 @@
 
 namespace b200gf {
 
-// library defaults (tools/spmm_sweep.cu measures the alternatives): 256 threads, default register budget,
-// L1::no_allocate gathers, next-row prefetch on
+// Library configuration, chosen from tools/spmm_sweep.cu on B200 (profiles/r1_spmm_sweep.md): 256 threads,
+// registers capped for 6 resident blocks/SM (48 warps: the kernel is latency-bound below that), gathered rows loaded
+// with an L2 evict_last policy and no L1 allocation (DRAM reads 7.9 GB -> 6.3 GB per hop at N=1M, C=64), no
+// next-row prefetch (it costs registers and measured slower).
 template <typename T, int VEC, int L, int U>
 static int launch_one(int sm_count, const CsrDev& A, int64_t n_rows, const T* src, int64_t src_ld, T* dst,
                       int64_t dst_ld, int C, cudaStream_t st) {
-  constexpr int THREADS = 256, MINB = 1, HINT = 1;
-  constexpr bool PF = true;
+  constexpr int THREADS = 256, MINB = sizeof(T) == 4 ? 6 : 4, HINT = 3;
+  constexpr bool PF = false;
   auto kern = spmm_hop_kernel<T, VEC, L, U, THREADS, MINB, HINT, PF>;
   const int n_chunks = (C + L * VEC - 1) / (L * VEC);
   const int64_t n_items = n_rows * n_chunks;
@@ -36,7 +38,7 @@ static int launch_one(int sm_count, const CsrDev& A, int64_t n_rows, const T* sr
   const int64_t cap = (int64_t)sm_count * occ;  // one resident wave: persistent warps stride over the items
   if (blocks > cap) blocks = cap;
   kern<<<(unsigned)blocks, THREADS, 0, st>>>(A.rowptr, A.col, reinterpret_cast<const T*>(A.val), src, src_ld, dst,
-                                             dst_ld, n_rows, C, n_chunks);
+                                             dst_ld, n_rows, C, n_chunks, 1.0f);
   LAUNCH_CHECK();
   return B200GF_OK;
 }

@@ -26,16 +26,19 @@ struct Acc {
   }
 };
 
-__device__ __forceinline__ uint64_t evict_last_policy() {
+// L2 cache policy: `frac` of the touched lines (chosen by address hash) get evict_last priority, the rest stay
+// evict_unchanged.  With the gathered feature matrix larger than the L2, a sticky subset that fits turns an LRU
+// thrash (measured 6 % L2 hit rate) into hits on that subset.
+__device__ __forceinline__ uint64_t evict_last_policy(float frac) {
   uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, %1;" : "=l"(pol) : "f"(frac));
   return pol;
 }
 
 // HINT 0: ld.global.nc (default policy)   1: + L1::no_allocate (gathered rows have no L1 reuse)
 // HINT 2: L1::no_allocate + L2::evict_last on the gathered rows (fight for L2 residency of the feature slab)
 template <typename T, int VEC, int HINT>
-__device__ __forceinline__ Acc<T, VEC> load_vec(const T* p) {
+__device__ __forceinline__ Acc<T, VEC> load_vec(const T* p, uint64_t pol) {
   Acc<T, VEC> a;
   if constexpr (VEC == 4) {
     float4 t;
@@ -46,7 +49,7 @@ __device__ __forceinline__ Acc<T, VEC> load_vec(const T* p) {
                    : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "l"(p));
     } else {
       asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-                   : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "l"(p), "l"(evict_last_policy()));
+                   : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "l"(p), "l"(pol));
     }
     a.v[0] = t.x; a.v[1] = t.y; a.v[2] = t.z; a.v[3] = t.w;
   } else if constexpr (VEC == 2) {
@@ -57,7 +60,7 @@ __device__ __forceinline__ Acc<T, VEC> load_vec(const T* p) {
       asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(t.x), "=d"(t.y) : "l"(p));
     } else {
       asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
-                   : "=d"(t.x), "=d"(t.y) : "l"(p), "l"(evict_last_policy()));
+                   : "=d"(t.x), "=d"(t.y) : "l"(p), "l"(pol));
     }
     a.v[0] = t.x; a.v[1] = t.y;
   } else {
@@ -66,12 +69,15 @@ __device__ __forceinline__ Acc<T, VEC> load_vec(const T* p) {
   return a;
 }
 
-template <typename T, int VEC>
+// SH 0: default store   1: st.global.cs (streaming: the result row is not re-read by this kernel)
+template <typename T, int VEC, int SH>
 __device__ __forceinline__ void store_vec(T* p, const Acc<T, VEC>& a) {
   if constexpr (VEC == 4) {
-    *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+    if constexpr (SH == 1) __stcs(reinterpret_cast<float4*>(p), make_float4(a.v[0], a.v[1], a.v[2], a.v[3]));
+    else *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
   } else if constexpr (VEC == 2) {
-    *reinterpret_cast<double2*>(p) = make_double2(a.v[0], a.v[1]);
+    if constexpr (SH == 1) __stcs(reinterpret_cast<double2*>(p), make_double2(a.v[0], a.v[1]));
+    else *reinterpret_cast<double2*>(p) = make_double2(a.v[0], a.v[1]);
   } else {
     p[0] = a.v[0];
   }
@@ -83,11 +89,16 @@ __device__ __forceinline__ V ld_stream(const V* p) { return __ldcs(p); }
 
 constexpr unsigned FULL = 0xffffffffu;
 
-template <typename T, int VEC, int L, int U, int THREADS, int MINB, int HINT, bool PF>
+template <typename T, int VEC, int L, int U, int THREADS, int MINB, int HINT, bool PF, int SH = 0>
 __global__ void __launch_bounds__(THREADS, MINB)
 spmm_hop_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                 const T* __restrict__ val, const T* __restrict__ src, int64_t src_ld,
-                T* __restrict__ dst, int64_t dst_ld, int64_t n_rows, int C, int n_chunks) {
+                T* __restrict__ dst, int64_t dst_ld, int64_t n_rows, int C, int n_chunks, float l2_frac) {
+  uint64_t pol = 0;
+  if constexpr (HINT == 2) pol = evict_last_policy(l2_frac);
+  if constexpr (HINT == 3) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  if constexpr (HINT == 4) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 0.5;" : "=l"(pol));
+  if constexpr (HINT == 5) asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.5;" : "=l"(pol));
   constexpr int S = 32 / L;  // neighbours gathered concurrently by one warp
   const int lane = threadIdx.x & 31;
   const int sub = lane / L;
@@ -149,7 +160,7 @@ spmm_hop_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ 
           const T ww = __shfl_sync(FULL, v, jj & 31);
           const bool ok = (jj < cnt) && col_ok;
           w[u] = ok ? ww : T(0);
-          if (ok) buf[u] = load_vec<T, VEC, HINT>(srcc + (int64_t)cc * src_ld);
+          if (ok) buf[u] = load_vec<T, VEC, HINT>(srcc + (int64_t)cc * src_ld, pol);
           else buf[u].zero();
         }
 #pragma unroll
@@ -165,7 +176,7 @@ spmm_hop_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ 
 #pragma unroll
       for (int i = 0; i < VEC; ++i) acc.v[i] += __shfl_xor_sync(FULL, acc.v[i], off);
     }
-    if (sub == 0 && col_ok) store_vec<T, VEC>(dst + row * dst_ld + cbase, acc);
+    if (sub == 0 && col_ok) store_vec<T, VEC, SH>(dst + row * dst_ld + cbase, acc);
 
     if (!has_next) break;
     item = next;

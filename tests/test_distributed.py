@@ -1,0 +1,158 @@
+"""Node-partitioned / feature-partitioned LSIGF (graph-neural-networks_b200/distributed.py).
+
+CPU: world_size-2 gloo runs with an oracle-backed `ops` (scipy / numpy stand-ins for the C-ABI building blocks) —
+exercises the partitioning, padding, in-place all-gather and reduce-scatter choreography against the fp64 oracle.
+GPU (-m gpu, needs >= 2 devices): the same through NCCL and the CUDA building blocks."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import lsigf_oracle as orc
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+class OracleOps:
+    """CPU stand-ins with the CudaOps interface (test infrastructure: uses scipy, mirrors include/b200gf.h semantics)."""
+
+    def __init__(self):
+        self.device = torch.device("cpu")
+
+    def make_plan_ops(self, fwd, bwd, n_rows, n_cols, dtype):
+        import scipy.sparse as sp
+        return {"fwd": [sp.csr_matrix((v, c, r), shape=(n_rows, n_cols)) for (r, c, v) in fwd]}
+
+    def make_plan_full(self, gso):
+        import scipy.sparse as sp
+        return {"fwd": [sp.csr_matrix((v, c, r), shape=(gso.N, gso.N)).T.tocsr() for (r, c, v) in gso.csr]}
+
+    def hop(self, plan, e, direction, src, dst, C):
+        assert direction == 0
+        out = plan["fwd"][e] @ src[:, :C].numpy()
+        dst[:, :C] = torch.from_numpy(np.ascontiguousarray(out))
+
+    def pack_taps(self, h, transpose):
+        F, E, K, G = h.shape
+        W = [h[:, :, 0, :].sum(1).t()]
+        for e in range(E):
+            for k in range(1, K):
+                W.append(h[:, e, k, :].t())
+        return torch.stack(W).contiguous()
+
+    def tap_contract(self, zs, W, bias, out, n_rows, B, P, Q, bias_per_node=0):
+        acc = torch.zeros(n_rows, B, Q, dtype=out.dtype)
+        for t, z in enumerate(zs):
+            acc += torch.einsum("nbp,pq->nbq", z[:n_rows, :B * P].reshape(n_rows, B, P), W[t])
+        if bias is not None:
+            acc += bias.view(1, 1, Q)
+        out[:n_rows, :B * Q] = acc.reshape(n_rows, B * Q)
+
+
+def _case(N=203, B=2, G=6, F=5, K=4, E=2, seed=3):
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    mats = []
+    for e in range(E):
+        m = sp.random(N, N, density=6.0 / N, format="csr", random_state=np.random.RandomState(seed + e),
+                      data_rvs=lambda n: rng.standard_normal(n))
+        mats.append(sp.csr_matrix(m / max(abs(m).sum(axis=1).max(), 1e-30)))
+    x = rng.standard_normal((B, G, N))
+    h = rng.uniform(-0.3, 0.3, (F, E, K, G))
+    b = rng.uniform(-0.3, 0.3, (F, 1))
+    return mats, x, h, b
+
+
+def _worker(rank, world, port, backend, mode, dtype_name, result_q):
+    import gnn_b200
+    from gnn_b200.distributed import PartitionedLSIGF
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dtype = getattr(torch, dtype_name)
+    if backend == "nccl":
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        ops = None
+    else:
+        dev = torch.device("cpu")
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        ops = OracleOps()
+    try:
+        mats, x, h, b = _case()
+        B, G, N = x.shape
+        F = h.shape[0]
+        gso = gnn_b200.SparseGSO.from_scipy(mats, dtype=dtype)
+        part = PartitionedLSIGF(gso, mode=mode, device=dev, ops=ops)
+        R = part.rows_per_rank
+        xn = torch.tensor(x, dtype=dtype).reshape(B * G, N).t().contiguous()       # node-major [N, B*G]
+        ht = torch.tensor(h, dtype=dtype, device=dev)
+        bt = torch.tensor(b, dtype=dtype, device=dev)
+        if mode == "nodes":
+            xp = torch.zeros(part.n_pad, B * G, dtype=dtype)
+            xp[:N] = xn
+            x_local = xp[part.r0:part.r1].to(dev)
+        else:
+            g0, g1 = part.feature_slice(G)
+            x_local = xn.view(N, B, G)[:, :, g0:g1].reshape(N, B * (g1 - g0)).contiguous().to(dev)
+        for _ in range(2):  # twice: buffers are reused across calls
+            y_local = part.forward(ht, x_local, bt, B=B)
+        assert tuple(y_local.shape) == (R, B * F)
+        ys = [torch.empty_like(y_local) for _ in range(world)]
+        dist.all_gather(ys, y_local.contiguous())
+        if rank == 0:
+            y = torch.cat(ys)[:N].cpu().double().numpy().reshape(N, B, F).transpose(1, 2, 0)
+            npd = np.float32 if dtype == torch.float32 else np.float64
+            import scipy.sparse as sp
+            mr = [sp.csr_matrix((m.data.astype(npd).astype(np.float64), m.indices, m.indptr), shape=m.shape) for m in mats]
+            r64 = lambda a: a.astype(npd).astype(np.float64)  # noqa: E731
+            y_ref = orc.lsigf_sparse(r64(h), mr, r64(x), r64(b))
+            result_q.put(float(np.abs(y - y_ref).max() / np.abs(y_ref).max()))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(backend, mode, dtype_name, world=2):
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    mp.spawn(_worker, args=(world, _free_port(), backend, mode, dtype_name, q), nprocs=world, join=True)
+    return q.get()
+
+
+@pytest.mark.parametrize("mode", ["nodes", "features"])
+def test_partitioned_gloo_world2(mode):
+    err = _run("gloo", mode, "float64")
+    assert err < 1e-12, err
+
+
+def test_row_slice_and_padding():
+    from gnn_b200.distributed import row_slice
+    rowptr = np.array([0, 2, 2, 5], dtype=np.int64)
+    col = np.array([0, 2, 0, 1, 2], dtype=np.int32)
+    val = np.arange(5, dtype=np.float64)
+    rp, c, v = row_slice((rowptr, col, val), 1, 3)
+    assert rp.tolist() == [0, 0, 3] and c.tolist() == [0, 1, 2] and v.tolist() == [2.0, 3.0, 4.0]
+    rp, c, v = row_slice((rowptr, col, val), 2, 5)      # rows 3, 4 do not exist: empty padding rows
+    assert rp.tolist() == [0, 3, 3, 3] and c.tolist() == [0, 1, 2]
+    rp, c, v = row_slice((rowptr, col, val), 4, 6)      # entirely padding
+    assert rp.tolist() == [0, 0, 0] and len(c) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["nodes", "features"])
+@pytest.mark.parametrize("dtype_name,tol", [("float32", 1e-4), ("float64", 1e-11)])
+def test_partitioned_nccl_world2(mode, dtype_name, tol):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    err = _run("nccl", mode, dtype_name)
+    assert err < tol, err

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <functional>
 #include <random>
 #include <vector>
 
@@ -22,9 +23,10 @@ struct Problem {
   double bytes;
 };
 
-template <int L, int U, int THREADS, int MINB, int HINT, bool PF>
-void run(const Problem& P, const char* name, int reps, double peak, int blocks_per_sm_override = 0, bool is_ref = false) {
-  auto kern = spmm_hop_kernel<float, 4, L, U, THREADS, MINB, HINT, PF>;
+template <int L, int U, int THREADS, int MINB, int HINT, bool PF, int SH = 0>
+double run(const Problem& P, const char* name, int reps, double peak, int blocks_per_sm_override = 0, bool is_ref = false,
+         float frac = 1.0f) {
+  auto kern = spmm_hop_kernel<float, 4, L, U, THREADS, MINB, HINT, PF, SH>;
   cudaFuncAttributes fa;
   CK(cudaFuncGetAttributes(&fa, kern));
   int occ = 0;
@@ -37,13 +39,13 @@ void run(const Problem& P, const char* name, int reps, double peak, int blocks_p
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   CK(cudaMemset(P.dst, 0xff, (size_t)P.N * P.C * 4));
   for (int i = 0; i < 2; ++i)
-    kern<<<(unsigned)blocks, THREADS>>>(P.rowptr, P.col, P.val, P.src, P.C, P.dst, P.C, P.N, P.C, n_chunks);
+    kern<<<(unsigned)blocks, THREADS>>>(P.rowptr, P.col, P.val, P.src, P.C, P.dst, P.C, P.N, P.C, n_chunks, frac);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   float best = 1e30f, sum = 0;
   for (int i = 0; i < reps; ++i) {
     CK(cudaEventRecord(e0));
-    kern<<<(unsigned)blocks, THREADS>>>(P.rowptr, P.col, P.val, P.src, P.C, P.dst, P.C, P.N, P.C, n_chunks);
+    kern<<<(unsigned)blocks, THREADS>>>(P.rowptr, P.col, P.val, P.src, P.C, P.dst, P.C, P.N, P.C, n_chunks, frac);
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -64,6 +66,7 @@ void run(const Problem& P, const char* name, int reps, double peak, int blocks_p
          name, fa.numRegs, occ, use, (long long)blocks, avg, best, P.bytes / (avg * 1e-3) / 1e9,
          P.bytes / (avg * 1e-3) / 1e9 / peak, maxdiff);
   fflush(stdout);
+  return avg;
 }
 
 int main(int argc, char** argv) {
@@ -115,42 +118,44 @@ int main(int argc, char** argv) {
     printf("cudaMemcpy D2D %zu MB: %.0f GB/s (read+write)\n", nb >> 20, 2.0 * nb * 10 / (ms * 1e-3) / 1e9);
   }
 
-  //   L   U  THR MINB HINT PF
+  // Each variant is run in 3 separate rounds (interleaved with the others) to expose run-to-run noise.
+  struct V { const char* name; std::function<double(bool)> fn; double ms[3]; };
+  std::vector<V> vs;
+#define ADD(NAME, ...) vs.push_back(V{NAME, [&](bool ref) { return run<__VA_ARGS__>(P, NAME, reps, peak, 0, ref, 1.0f); }, {0, 0, 0}})
+  //                                   L   U  THR MINB HINT PF SH
   if (C <= 64) {
-    run<16, 4, 256, 1, 1, true>(P, "L16 U4 t256 mb1 noalloc PF", reps, peak, 0, true);
-    run<16, 4, 256, 1, 0, true>(P, "L16 U4 t256 mb1 ldg PF", reps, peak);
-    run<16, 4, 256, 1, 2, true>(P, "L16 U4 t256 mb1 evict_last PF", reps, peak);
-    run<16, 4, 256, 1, 1, false>(P, "L16 U4 t256 mb1 noalloc noPF", reps, peak);
-    run<16, 2, 256, 1, 1, true>(P, "L16 U2 t256 mb1 noalloc PF", reps, peak);
-    run<16, 8, 256, 1, 1, true>(P, "L16 U8 t256 mb1 noalloc PF", reps, peak);
-    run<16, 4, 256, 5, 1, true>(P, "L16 U4 t256 mb5 noalloc PF", reps, peak);
-    run<16, 4, 256, 6, 1, true>(P, "L16 U4 t256 mb6 noalloc PF", reps, peak);
-    run<16, 4, 256, 8, 1, true>(P, "L16 U4 t256 mb8 noalloc PF", reps, peak);
-    run<16, 2, 256, 8, 1, true>(P, "L16 U2 t256 mb8 noalloc PF", reps, peak);
-    run<16, 8, 256, 4, 1, true>(P, "L16 U8 t256 mb4 noalloc PF", reps, peak);
-    run<16, 8, 256, 3, 1, true>(P, "L16 U8 t256 mb3 noalloc PF", reps, peak);
-    run<16, 4, 128, 1, 1, true>(P, "L16 U4 t128 mb1 noalloc PF", reps, peak);
-    run<16, 4, 512, 1, 1, true>(P, "L16 U4 t512 mb1 noalloc PF", reps, peak);
-    run<16, 4, 1024, 1, 1, true>(P, "L16 U4 t1024 mb1 noalloc PF", reps, peak);
-    // occupancy sensitivity at fixed code: cap resident blocks per SM
-    run<16, 4, 256, 1, 1, true>(P, "L16 U4 t256 mb1 noalloc PF cap2", reps, peak, 2);
-    run<16, 4, 256, 1, 1, true>(P, "L16 U4 t256 mb1 noalloc PF cap3", reps, peak, 3);
-    // column split: two passes over 32-column halves / four over 16-column quarters (L2 residency experiment)
-    run<8, 4, 256, 1, 1, true>(P, "L8  U4 (2 x 32-col passes)", reps, peak);
-    run<8, 8, 256, 1, 1, true>(P, "L8  U8 (2 x 32-col passes)", reps, peak);
-    run<4, 8, 256, 1, 1, true>(P, "L4  U8 (4 x 16-col passes)", reps, peak);
-    run<4, 8, 256, 1, 2, true>(P, "L4  U8 (4 x 16-col) evict_last", reps, peak);
+    ADD("noalloc PF   mb6",            16, 4, 256, 6, 1, true);
+    ADD("noalloc noPF mb6",            16, 4, 256, 6, 1, false);
+    ADD("ldg     noPF mb6",            16, 4, 256, 6, 0, false);
+    ADD("ELimm1  PF   mb1(64r)",       16, 4, 256, 1, 3, true);
+    ADD("ELimm1  PF   mb6",            16, 4, 256, 6, 3, true);
+    ADD("ELimm1  noPF mb6",            16, 4, 256, 6, 3, false);
+    ADD("ELimm1  noPF mb5",            16, 4, 256, 5, 3, false);
+    ADD("ELimm1  noPF mb4",            16, 4, 256, 4, 3, false);
+    ADD("ELreg1  noPF mb6",            16, 4, 256, 6, 2, false);
+    ADD("ELimm.5 noPF mb6",            16, 4, 256, 6, 4, false);
+    ADD("EL.5/EF noPF mb6",            16, 4, 256, 6, 5, false);
+    ADD("ELimm1  noPF mb6 st.cs",      16, 4, 256, 6, 3, false, 1);
+    ADD("ELimm1  noPF mb8 U2",         16, 2, 256, 8, 3, false);
+    ADD("ELimm1  noPF t128 mb12",      16, 4, 128, 12, 3, false);
+    ADD("ELimm1  noPF t512 mb3",       16, 4, 512, 3, 3, false);
   } else {
-    run<32, 4, 256, 1, 1, true>(P, "L32 U4 t256 mb1 noalloc PF", reps, peak, 0, true);
-    run<32, 4, 256, 1, 0, true>(P, "L32 U4 t256 mb1 ldg PF", reps, peak);
-    run<32, 4, 256, 1, 2, true>(P, "L32 U4 t256 mb1 evict_last PF", reps, peak);
-    run<32, 8, 256, 1, 1, true>(P, "L32 U8 t256 mb1 noalloc PF", reps, peak);
-    run<32, 2, 256, 1, 1, true>(P, "L32 U2 t256 mb1 noalloc PF", reps, peak);
-    run<32, 4, 256, 6, 1, true>(P, "L32 U4 t256 mb6 noalloc PF", reps, peak);
-    run<32, 8, 256, 4, 1, true>(P, "L32 U8 t256 mb4 noalloc PF", reps, peak);
-    run<32, 4, 512, 1, 1, true>(P, "L32 U4 t512 mb1 noalloc PF", reps, peak);
-    run<16, 4, 256, 1, 1, true>(P, "L16 U4 (64-col chunks)", reps, peak);
-    run<8, 8, 256, 1, 1, true>(P, "L8 U8 (32-col chunks)", reps, peak);
+    ADD("noalloc PF   mb6",            32, 4, 256, 6, 1, true);
+    ADD("noalloc noPF mb6",            32, 4, 256, 6, 1, false);
+    ADD("ELimm1  PF   mb4",            32, 4, 256, 4, 3, true);
+    ADD("ELimm1  noPF mb4",            32, 4, 256, 4, 3, false);
+    ADD("ELimm1  noPF mb6",            32, 4, 256, 6, 3, false);
+    ADD("ELreg1  noPF mb6",            32, 4, 256, 6, 2, false);
+    ADD("ELimm1  noPF mb6 st.cs",      32, 4, 256, 6, 3, false, 1);
+  }
+  for (int round = 0; round < 3; ++round)
+    for (size_t i = 0; i < vs.size(); ++i) vs[i].ms[round] = vs[i].fn(round == 0 && i == 0);
+  printf("\nsummary (avg ms per round, algorithmic GB/s of the median round, frac of %.0f GB/s)\n", peak);
+  for (auto& v : vs) {
+    double m[3] = {v.ms[0], v.ms[1], v.ms[2]};
+    std::sort(m, m + 3);
+    printf("%-28s %.3f %.3f %.3f   median %.3f ms  %.0f GB/s  frac %.3f\n", v.name, v.ms[0], v.ms[1], v.ms[2], m[1],
+           P.bytes / (m[1] * 1e-3) / 1e9, P.bytes / (m[1] * 1e-3) / 1e9 / peak);
   }
   return 0;
 }
