@@ -70,28 +70,63 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """Samples SM clock / throttle reasons DURING the timed region (nvidia-smi, 200 ms)."""
+    """Samples SM clock and throttle reasons DURING the timed region (NVML every 10 ms; nvidia-smi fallback)."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index=0):
         self.index = index
-        self.samples = []
+        self.sm = []
+        self.sm_max = None
+        self.reasons = set()
         self._stop = threading.Event()
         self._t = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)  # all GPUs of the box are visible: NVML index == CUDA index
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
 
-    def _run(self):
+    def _sample_nvml(self):
+        n = self._nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        for k, b in bits.items():
+            if r & b:
+                self.reasons.add(k)
+
+    def _sample_smi(self):
         import subprocess
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout
+        f = [v.strip() for v in out.strip().split(",")]
+        if len(f) >= 6:
+            self.sm.append(float(f[0]))
+            self.sm_max = float(f[1])
+            for i, k in enumerate(self.NAMES):
+                if f[2 + i].lower().startswith("active"):
+                    self.reasons.add(k)
+
+    def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [v.strip() for v in out.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(f)
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.01 if self._nvml is not None else 0.2)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -103,13 +138,11 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(float(s[0]) for s in self.samples)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(sm)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unsampled"]}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(sm), "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -241,6 +274,20 @@ def run_gpu_arm(args, w):
 
         with torch.no_grad():
             ms_e2e = timed(e2e_step, max(3, args.steps // 2), 2)
+        # forward + backward (reported beside the headline; SURVEY.md §8d asks for both)
+        xg = x.clone().requires_grad_(True)
+        hg = h.clone().requires_grad_(True)
+        bg = b.clone().requires_grad_(True)
+        dy = torch.randn(B, F, N, generator=g).to(dev)
+
+        def fwd_bwd():
+            xg.grad = hg.grad = bg.grad = None
+            gnn_b200.LSIGF(hg, gso, xg, bg).backward(dy)
+
+        ms_fb = timed(fwd_bwd, max(3, args.steps // 2), 2)
+        out["fwd_bwd"] = {"ms_per_step": ms_fb, "unit": "edge-feature-op/s",
+                          "value": float(gso.nnz()) * (K - 1) * B * (G + F) / (ms_fb * 1e-3),
+                          "note": "forward hops on B*G columns + backward hops on B*F columns per step"}
         C = B * G
         hop_bytes = hop_algorithmic_bytes(nnz_e, N, C)
         hop_avg_ms = float(np.mean(hop_ms)) if len(hop_ms) else float("nan")
@@ -332,7 +379,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="er1m", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="nodes", choices=["nodes", "features"])
+    ap.add_argument("--mode", default="features", choices=["nodes", "features"],
+                    help="multi-GPU sharding (DESIGN.md §4): feature columns (default) or node rows")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)

@@ -65,6 +65,16 @@ int launch_bias_grad(int dtype, int64_t n_rows, int B, int F, const void* dy, in
                      int bias_per_node, void* scratch, size_t scratch_bytes, cudaStream_t st);
 size_t bias_grad_scratch_bytes(int dtype, int64_t n_rows, int B, int F);
 
+// tensor-core (tcgen05, 3xTF32) contraction, tc_contract.cu
+size_t tc_contract_scratch_bytes(int T, int P, int Q);
+bool tc_contract_eligible(int dtype, int64_t n_rows, int B, int P, int Q, int T, const void* const* zs,
+                          const int64_t* z_ld, const void* out, int64_t out_ld, int accumulate);
+int launch_pack_taps_split(const void* h, void* whi_wlo, int F, int E, int K, int G, int to_input, cudaStream_t st);
+int launch_split_w(const void* W, void* whi_wlo, int T, int P, int Q, cudaStream_t st);
+int launch_tc_contract(int sm_count, int64_t n_rows, int B, int P, int Q, int T, const void* const* zs,
+                       const void* whi_wlo, const void* bias, int bias_per_node, void* out, int64_t out_ld,
+                       cudaStream_t st);
+
 int launch_pack_taps(int dtype, const void* h, void* W, int F, int E, int K, int G, int transpose_taps,
                      cudaStream_t st);
 int launch_to_node_major(int dtype, const void* src, void* dst, int64_t dst_ld, int64_t N, int C,

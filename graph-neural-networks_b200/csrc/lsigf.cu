@@ -40,7 +40,7 @@ FwdWs carve_fwd(const b200gf_plan* p, void* ws, int B, int G, int F, int K, int 
   FwdWs w;
   if (x_layout == B200GF_FEATURE_MAJOR) w.xn = c.take((size_t)p->n_cols * ldc * es);
   w.z = c.take((size_t)p->E * (K - 1) * p->n_cols * ldc * es);
-  w.W = c.take((size_t)T * G * F * es);
+  w.W = c.take((size_t)2 * T * G * F * es);  // x2: hi / lo operand copies of the tensor-core path
   if (y_layout == B200GF_FEATURE_MAJOR) w.yn = c.take((size_t)p->n_rows * ldf * es);
   w.bytes = c.off;
   return w;
@@ -71,7 +71,7 @@ BwdWs carve_bwd(const b200gf_plan* p, void* ws, int B, int G, int F, int K, int 
     w.dxn = c.take((size_t)p->n_rows * ldc * es);
   }
   w.v = c.take((size_t)p->E * (K - 1) * p->n_cols * ldf * es);
-  w.W = c.take((size_t)T * G * F * es);
+  w.W = c.take((size_t)2 * T * G * F * es);
   w.tg_bytes = tap_grad_scratch_bytes(p->dtype, p->n_rows, B, G, F, T);
   w.tg = c.take(w.tg_bytes);
   w.bg_bytes = bias_grad_scratch_bytes(p->dtype, p->n_rows, B, F);
@@ -166,8 +166,6 @@ int b200gf_forward(const b200gf_plan* plan, const void* x, int x_layout, int64_t
     x0 = w.xn;
     x0_ld = ldc;
   }
-  if ((rc = launch_pack_taps(dt, h, w.W, F, E, K, G, 0, st))) return rc;
-
   std::vector<const void*> zs(T);
   std::vector<int64_t> zld(T);
   zs[0] = x0;
@@ -187,8 +185,16 @@ int b200gf_forward(const b200gf_plan* plan, const void* x, int x_layout, int64_t
   }
   void* yo = y_layout == B200GF_NODE_MAJOR ? y : w.yn;
   const int64_t yo_ld = y_layout == B200GF_NODE_MAJOR ? y_ld : ldf;
-  if ((rc = launch_tap_contract(dt, N, B, G, F, T, zs.data(), zld.data(), w.W, bias, bias_per_node, yo, yo_ld, 0, st)))
-    return rc;
+  if (tc_contract_eligible(dt, N, B, G, F, T, zs.data(), zld.data(), yo, yo_ld, 0)) {
+    // tensor cores: tcgen05 3xTF32, operands K-major: W[t][f][g]
+    if ((rc = launch_pack_taps_split(h, w.W, F, E, K, G, 0, st))) return rc;
+    if ((rc = launch_tc_contract(plan->sm_count, N, B, G, F, T, zs.data(), w.W, bias, bias_per_node, yo, yo_ld, st)))
+      return rc;
+  } else {
+    if ((rc = launch_pack_taps(dt, h, w.W, F, E, K, G, 0, st))) return rc;
+    if ((rc = launch_tap_contract(dt, N, B, G, F, T, zs.data(), zld.data(), w.W, bias, bias_per_node, yo, yo_ld, 0, st)))
+      return rc;
+  }
   if (y_layout == B200GF_FEATURE_MAJOR)
     if ((rc = launch_to_feature_major(dt, w.yn, ldf, y, N, (int)CF, st))) return rc;
   return B200GF_OK;
@@ -258,11 +264,16 @@ int b200gf_backward(const b200gf_plan* plan, const void* dy, int dy_layout, int6
     }
   }
   if (dx) {
-    if ((rc = launch_pack_taps(dt, h, w.W, F, E, K, G, 1, st))) return rc;  // W[t][f][g]
     void* dxo = dx_layout == B200GF_NODE_MAJOR ? dx : w.dxn;
     const int64_t dxo_ld = dx_layout == B200GF_NODE_MAJOR ? dx_ld : ldc;
-    if ((rc = launch_tap_contract(dt, N, B, F, G, T, vs.data(), vld.data(), w.W, nullptr, 0, dxo, dxo_ld, 0, st)))
-      return rc;
+    if (tc_contract_eligible(dt, N, B, F, G, T, vs.data(), vld.data(), dxo, dxo_ld, 0)) {
+      if ((rc = launch_pack_taps_split(h, w.W, F, E, K, G, 1, st))) return rc;  // K-major W[t][g][f]
+      if ((rc = launch_tc_contract(plan->sm_count, N, B, F, G, T, vs.data(), w.W, nullptr, 0, dxo, dxo_ld, st))) return rc;
+    } else {
+      if ((rc = launch_pack_taps(dt, h, w.W, F, E, K, G, 1, st))) return rc;  // W[t][f][g]
+      if ((rc = launch_tap_contract(dt, N, B, F, G, T, vs.data(), vld.data(), w.W, nullptr, 0, dxo, dxo_ld, 0, st)))
+        return rc;
+    }
     if (dx_layout == B200GF_FEATURE_MAJOR)
       if ((rc = launch_to_feature_major(dt, w.dxn, ldc, dx, N, (int)C, st))) return rc;
   }

@@ -424,10 +424,23 @@ int b200gf_pack_taps(int dtype, const void* h, void* W, int F, int E, int K, int
 
 int b200gf_tap_contract(int dtype, int64_t n_rows, int B, int P, int Q, int T, const void* const* zs,
                         const int64_t* z_ld, const void* W, const void* bias, int bias_per_node, void* out,
-                        int64_t out_ld, int accumulate, void* stream) {
-  return b200gf::launch_tap_contract(dtype, n_rows, B, P, Q, T, zs, z_ld, W, bias, bias_per_node, out, out_ld,
-                                     accumulate, (cudaStream_t)stream);
+                        int64_t out_ld, int accumulate, void* scratch, size_t scratch_bytes, void* stream) {
+  using namespace b200gf;
+  if (n_rows < 0 || B <= 0 || P <= 0 || Q <= 0 || T <= 0 || !zs || !z_ld || !W || !out) return B200GF_EINVAL;
+  if (scratch && scratch_bytes >= tc_contract_scratch_bytes(T, P, Q) && (reinterpret_cast<uintptr_t>(scratch) & 15) == 0 &&
+      tc_contract_eligible(dtype, n_rows, B, P, Q, T, zs, z_ld, out, out_ld, accumulate)) {
+    int dev = 0, sms = 148;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int rc = launch_split_w(W, scratch, T, P, Q, (cudaStream_t)stream);
+    if (rc) return rc;
+    return launch_tc_contract(sms, n_rows, B, P, Q, T, zs, scratch, bias, bias_per_node, out, out_ld, (cudaStream_t)stream);
+  }
+  return launch_tap_contract(dtype, n_rows, B, P, Q, T, zs, z_ld, W, bias, bias_per_node, out, out_ld, accumulate,
+                             (cudaStream_t)stream);
 }
+
+size_t b200gf_tap_contract_scratch_bytes(int T, int P, int Q) { return b200gf::tc_contract_scratch_bytes(T, P, Q); }
 
 int b200gf_tap_grad(int dtype, int64_t n_rows, int B, int P, int Q, int T, const void* A, int64_t a_ld,
                     const void* const* vs, const int64_t* v_ld, void* dW, void* scratch, size_t scratch_bytes,

@@ -78,10 +78,12 @@ class CudaOps:
 
     def tap_contract(self, zs, W, bias, out, n_rows, B, P, Q, bias_per_node=0):
         T = len(zs)
+        sb = self.lib.b200gf_tap_contract_scratch_bytes(T, P, Q)
+        scratch = torch.empty(sb, dtype=torch.uint8, device=out.device)
         _cabi.check(self.lib.b200gf_tap_contract(
             _ENUM[out.dtype], n_rows, B, P, Q, T, _cabi.ptr_array([z.data_ptr() for z in zs]),
             _cabi.i64_array([z.stride(0) for z in zs]), W.data_ptr(), None if bias is None else bias.data_ptr(),
-            bias_per_node, out.data_ptr(), out.stride(0), 0, self._st()))
+            bias_per_node, out.data_ptr(), out.stride(0), 0, scratch.data_ptr(), sb, self._st()))
 
 
 class PartitionedLSIGF:

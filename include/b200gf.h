@@ -138,11 +138,16 @@ int b200gf_hop(const b200gf_plan* plan, int e, int direction,
 
 /* tap contraction: out[n, b*Q + q] = bias + sum_t sum_p Z_t[n, b*P + p] * W[t][p][q]   for n < n_rows.
  * zs: HOST array of T device pointers (node-major, stride z_ld[t]); W: device [T,P,Q] contiguous;
- * bias NULL / [Q] / [Q, n_rows] (bias_per_node).  accumulate != 0 adds to the existing `out`. */
+ * bias NULL / [Q] / [Q, n_rows] (bias_per_node).  accumulate != 0 adds to the existing `out`.
+ * scratch (optional, b200gf_tap_contract_scratch_bytes(T,P,Q) bytes, 16-byte aligned): when given, FP32 problems
+ * with P % 32 == 0, Q % 16 == 0, Q <= 256, T <= 16, z_ld == B*P and accumulate == 0 run on the tensor cores
+ * (tcgen05 kind::tf32 with hi/lo error compensation, "3xTF32"); everything else uses the FP32/FP64 FMA kernel. */
 int b200gf_tap_contract(int dtype, int64_t n_rows, int B, int P, int Q, int T,
                         const void* const* zs, const int64_t* z_ld, const void* W,
                         const void* bias, int bias_per_node,
-                        void* out, int64_t out_ld, int accumulate, void* stream);
+                        void* out, int64_t out_ld, int accumulate,
+                        void* scratch, size_t scratch_bytes, void* stream);
+size_t b200gf_tap_contract_scratch_bytes(int T, int P, int Q);
 
 /* tap gradient: dW[t][p][q] = sum_{n<n_rows, b} A[n, b*P + p] * Vs_t[n, b*Q + q]   (deterministic two-pass)
  * partial: device scratch of b200gf_tap_grad_scratch_bytes(...) bytes. */

@@ -160,7 +160,7 @@ def test_layout_and_tap_blocks():
         ldo = gnn_b200.padded_ld(B * F, dtype)
         out = torch.zeros(N, ldo, dtype=dtype, device="cuda")
         rc = lib.b200gf_tap_contract(enum, N, B, G, F, T, cabi.ptr_array([z.data_ptr() for z in zs]),
-                                     cabi.i64_array([ld] * T), W.data_ptr(), bias.data_ptr(), 0, out.data_ptr(), ldo, 0, st)
+                                     cabi.i64_array([ld] * T), W.data_ptr(), bias.data_ptr(), 0, out.data_ptr(), ldo, 0, None, 0, st)
         assert rc == 0
         Z = torch.stack([z[:, :C].reshape(N, B, G) for z in zs]).double()
         ref = torch.einsum("tnbg,tgf->nbf", Z, W.double()) + bias.double()
@@ -183,3 +183,55 @@ def test_layout_and_tap_blocks():
         assert lib.b200gf_pack_taps(enum, h.data_ptr(), Wp.data_ptr(), F, E, K, G, 0, st) == 0
         assert torch.allclose(Wp[0], h[:, :, 0, :].sum(1).t())
         assert torch.equal(Wp[1 + 1 * (K - 1) + 1], h[:, 1, 2, :].t())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,B,P,Q,T,bias_mode", [
+    (1000, 1, 64, 64, 5, "q"),        # headline layer shape, ragged last tile
+    (128, 1, 32, 16, 1, None),        # one tile, one chunk
+    (777, 3, 32, 32, 9, "q"),         # B > 1 (cfg4 shape: E=4, K=3 -> T=9)
+    (2500, 2, 64, 128, 3, "node"),    # wide output, per-node bias
+    (4096, 1, 96, 256, 2, "q"),       # P = 3 chunks, Q = 256 (2 pipeline stages)
+    (50000, 1, 64, 64, 5, "q"),       # several tiles per CTA: accumulator double-buffering and ring wrap-around
+])
+def test_tensor_core_tap_contract(N, B, P, Q, T, bias_mode):
+    """tcgen05 3xTF32 contraction (tc_contract.cu) vs an fp64 einsum; must sit at FP32 accuracy, far inside 1e-4."""
+    import gnn_b200
+    cabi = gnn_b200._cabi
+    lib = cabi.load()
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device="cuda").manual_seed(N + P + Q)
+    ld = B * P
+    zs = [torch.randn(N, ld, device="cuda", generator=g) * (1.0 + t) for t in range(T)]
+    W = (torch.rand(T, P, Q, device="cuda", generator=g) * 2 - 1) / np.sqrt(P * T)
+    bias = None
+    if bias_mode == "q":
+        bias = torch.randn(Q, device="cuda", generator=g)
+    elif bias_mode == "node":
+        bias = torch.randn(Q, N, device="cuda", generator=g)
+    ldo = B * Q
+    out = torch.full((N, ldo), float("nan"), device="cuda")
+    sb = lib.b200gf_tap_contract_scratch_bytes(T, P, Q)
+    scratch = torch.empty(sb, dtype=torch.uint8, device="cuda")
+    rc = lib.b200gf_tap_contract(cabi.F32, N, B, P, Q, T, cabi.ptr_array([z.data_ptr() for z in zs]),
+                                 cabi.i64_array([ld] * T), W.data_ptr(), None if bias is None else bias.data_ptr(),
+                                 1 if bias_mode == "node" else 0, out.data_ptr(), ldo, 0, scratch.data_ptr(), sb, st)
+    assert rc == 0, lib.b200gf_strerror(rc)
+    torch.cuda.synchronize()
+    Z = torch.stack([z.view(N, B, P) for z in zs]).double()
+    ref = torch.einsum("tnbp,tpq->nbq", Z, W.double())
+    if bias_mode == "q":
+        ref = ref + bias.double()
+    elif bias_mode == "node":
+        ref = ref + bias.double().t()[:, None, :]
+    err = _rel(out.view(N, B, Q).cpu().numpy(), ref.cpu().numpy())
+    # same problem through the FMA kernel (no scratch): the two paths must agree to FP32 rounding
+    out2 = torch.empty_like(out)
+    rc = lib.b200gf_tap_contract(cabi.F32, N, B, P, Q, T, cabi.ptr_array([z.data_ptr() for z in zs]),
+                                 cabi.i64_array([ld] * T), W.data_ptr(), None if bias is None else bias.data_ptr(),
+                                 1 if bias_mode == "node" else 0, out2.data_ptr(), ldo, 0, None, 0, st)
+    assert rc == 0
+    err_fma = _rel(out2.view(N, B, Q).cpu().numpy(), ref.cpu().numpy())
+    print("tc err %.2e  fma err %.2e" % (err, err_fma))
+    assert err < 5e-6, err
+    assert err_fma < 5e-6, err_fma
