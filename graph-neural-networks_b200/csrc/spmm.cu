@@ -43,6 +43,27 @@ static int launch_one(int sm_count, const CsrDev& A, int64_t n_rows, const T* sr
   return B200GF_OK;
 }
 
+// narrow rows (<= 128 bytes): several rows per warp (spmm_hop_multirow_kernel); geometry from the small-C sweep
+// (profiles/r1_spmm_sweep_smallC.log: C = 8 0.39 -> 0.19 ms, C = 16 0.48 -> 0.34 ms, C = 32 0.75 -> 0.68 ms at N = 1M)
+template <typename T, int VEC, int L, int GS, int U, int MINB>
+static int launch_multirow(int sm_count, const CsrDev& A, int64_t n_rows, const T* src, int64_t src_ld, T* dst,
+                           int64_t dst_ld, int C, cudaStream_t st) {
+  constexpr int THREADS = 256, HINT = 3;
+  auto kern = spmm_hop_multirow_kernel<T, VEC, L, GS, U, THREADS, MINB, HINT>;
+  if (n_rows == 0) return B200GF_OK;
+  constexpr int rows_per_block = (THREADS / 32) * (32 / GS);
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, 0));
+  if (occ < 1) occ = 1;
+  int64_t blocks = (n_rows + rows_per_block - 1) / rows_per_block;
+  const int64_t cap = (int64_t)sm_count * occ;
+  if (blocks > cap) blocks = cap;
+  kern<<<(unsigned)blocks, THREADS, 0, st>>>(A.rowptr, A.col, reinterpret_cast<const T*>(A.val), src, src_ld, dst,
+                                             dst_ld, n_rows, C);
+  LAUNCH_CHECK();
+  return B200GF_OK;
+}
+
 template <typename T>
 static int launch_typed(int sm_count, const CsrDev& A, int64_t n_rows, const void* src_, int64_t src_ld,
                         void* dst_, int64_t dst_ld, int C, cudaStream_t st) {
@@ -54,10 +75,11 @@ static int launch_typed(int sm_count, const CsrDev& A, int64_t n_rows, const voi
                       ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
   if (!vec_ok) return launch_one<T, 1, 32, 4>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st);
   const int nv = Cv / VEC;  // 16-byte vectors per row
-  if (nv <= 1) return launch_one<T, VEC, 1, 2>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st);
-  if (nv <= 2) return launch_one<T, VEC, 2, 2>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st);
-  if (nv <= 4) return launch_one<T, VEC, 4, 2>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st);
-  if (nv <= 8) return launch_one<T, VEC, 8, 4>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st);
+  constexpr int MB = sizeof(T) == 4 ? 6 : 4;
+  if (nv <= 1) return launch_multirow<T, VEC, 1, 8, 1, MB>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st);
+  if (nv <= 2) return launch_multirow<T, VEC, 2, 8, 2, MB>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st);
+  if (nv <= 4) return launch_multirow<T, VEC, 4, 16, 2, sizeof(T) == 4 ? 8 : 4>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st);
+  if (nv <= 8) return launch_multirow<T, VEC, 8, 32, 4, MB>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st);
   if (nv <= 16) return launch_one<T, VEC, 16, 4>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st);
   return launch_one<T, VEC, 32, 4>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st);
 }

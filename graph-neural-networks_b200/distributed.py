@@ -9,8 +9,10 @@ Two shardings of  y = sum_{e,k} (x S_e^k) h_{e,k} + b :
                    row-local.  This is the sharding BASELINE.json names.
   mode="features"  The graph is replicated and the B*G feature columns are split: a hop never mixes columns, so the
                    K-1 hops need NO communication and each rank's gathered slab (N x C/P) shrinks towards the L2.
-                   One reduce-scatter of the partial [N, B*F] outputs (the g-sum of the contraction is split across
-                   ranks) ends the call.  The right choice whenever S fits on each GPU (SURVEY §8e "column split").
+                   Every shifted slice z_k is sent to the ranks that own its node rows with an asynchronous NCCL
+                   all-to-all that overlaps the next hop; one row-local contraction over all E*K*G inputs ends the
+                   call (output sharded by node rows).  The right choice whenever S fits on each GPU (SURVEY §8e
+                   "column split"); a reduce-scatter variant covers G not divisible by the world size.
 
 The arithmetic goes through `ops` (the C-ABI building blocks b200gf_hop / b200gf_tap_contract on CUDA).  The
 world_size-2 gloo tests inject an oracle-backed `ops` to exercise the partitioning / collective choreography on CPU;
@@ -178,6 +180,47 @@ class PartitionedLSIGF:
         return y[:, :B * F]
 
     def _forward_features(self, h, x_cols, b, B):
+        """Column-sharded hops (no communication inside a hop) + an all-to-all of every shifted slice to the rank that
+        owns the node rows, overlapped with the following hops; then ONE row-local contraction over all E*K*G inputs.
+        Bytes on NVLink per rank: T * N * B*(G/P) * s * (P-1)/P, all but the last slice hidden behind compute."""
+        F, E, K, G = h.shape
+        P = self.world
+        if G % P != 0:
+            return self._forward_features_rs(h, x_cols, b, B)
+        Gl = G // P
+        Cl = B * Gl
+        R = self.rows_per_rank
+        T = 1 + E * (K - 1)
+        assert x_cols.shape[0] == self.N and x_cols.shape[1] == Cl
+        ld = _pad_ld(Cl, self.dtype)
+        z0 = self._buffers(("fz0", Cl), (self.n_pad, ld))
+        z0[:self.N, :Cl].copy_(x_cols)
+        recv = self._buffers(("frecv", T, Cl), (T, P, R, ld))   # recv[t, p]: my rows, column slice of rank p
+        works = [all_to_all_rows(recv[0], z0, self.group)]
+        for e in range(E):
+            src = z0
+            for k in range(1, K):
+                t = 1 + e * (K - 1) + (k - 1)
+                dst = self._buffers(("fz", e, k, Cl), (self.n_pad, ld))
+                self.ops.hop(self.plan, e, _cabi.HOP_FWD, src, dst, Cl)
+                works.append(all_to_all_rows(recv[t], dst, self.group))   # overlaps the next hop
+                src = dst
+        for w in works:
+            if w is not None:
+                w.wait()
+        # [T, P, R, B, Gl] -> row-local operand [R, B, T*G] (column t*G + p*Gl + gl == t*G + g)
+        zrow = recv[:, :, :, :Cl].reshape(T, P, R, B, Gl).permute(2, 3, 0, 1, 4).reshape(R, B * T * G)
+        W = self.ops.pack_taps(h, False).reshape(1, T * G, F)
+        y = torch.empty((R, _pad_ld(B * F, self.dtype)), dtype=self.dtype, device=self.device)
+        bias = None
+        if b is not None:
+            assert b.shape[1] == 1, "per-node bias is not supported by the partitioned path"
+            bias = b.contiguous()
+        self.ops.tap_contract([zrow], W, bias, y, R, B, T * G, F)
+        return y[:, :B * F]
+
+    def _forward_features_rs(self, h, x_cols, b, B):
+        """Fallback when G is not divisible by the world size: partial contraction + reduce-scatter of [N, B*F]."""
         F, E, K, G = h.shape
         g0, g1 = self.feature_slice(G)
         Gl = g1 - g0
@@ -210,6 +253,20 @@ class PartitionedLSIGF:
             y = y.view(R, B, F) + b.view(1, 1, F)
             y = y.reshape(R, B * F)
         return y
+
+
+def all_to_all_rows(out, inp, group=None):
+    """out[p] (my row block as held by rank p) <- rank p's inp row block `rank`.  inp is [P*R, ld], out [P, R, ld].
+    NCCL: asynchronous all_to_all_single (returns the Work handle).  gloo (CPU tests): all-gather + slice."""
+    if dist.get_backend(group) == "nccl":
+        return dist.all_to_all_single(out.view(-1), inp.view(-1), group=group, async_op=True)
+    P = dist.get_world_size(group)
+    r = dist.get_rank(group)
+    bufs = [torch.empty_like(inp) for _ in range(P)]
+    dist.all_gather(bufs, inp.contiguous(), group=group)
+    for p in range(P):
+        out[p].copy_(bufs[p].view(P, out.shape[1], out.shape[2])[r])
+    return None
 
 
 def reduce_scatter_rows(out_rows, full, group=None):

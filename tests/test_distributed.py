@@ -39,8 +39,9 @@ class OracleOps:
 
     def hop(self, plan, e, direction, src, dst, C):
         assert direction == 0
-        out = plan["fwd"][e] @ src[:, :C].numpy()
-        dst[:, :C] = torch.from_numpy(np.ascontiguousarray(out))
+        A = plan["fwd"][e]                      # like b200gf_hop: reads n_cols rows of src, writes n_rows rows of dst
+        out = A @ src[:A.shape[1], :C].numpy()
+        dst[:A.shape[0], :C] = torch.from_numpy(np.ascontiguousarray(out))
 
     def pack_taps(self, h, transpose):
         F, E, K, G = h.shape

@@ -69,6 +69,45 @@ double run(const Problem& P, const char* name, int reps, double peak, int blocks
   return avg;
 }
 
+// multi-row-per-warp kernel for narrow rows
+template <int L, int GS, int U, int MINB, int HINT>
+double run_mr(const Problem& P, const char* name, int reps, double peak) {
+  constexpr int THREADS = 256;
+  auto kern = spmm_hop_multirow_kernel<float, 4, L, GS, U, THREADS, MINB, HINT>;
+  cudaFuncAttributes fa;
+  CK(cudaFuncGetAttributes(&fa, kern));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, 0));
+  const int rpw = 32 / GS;
+  const int64_t warps_needed = (P.N + rpw - 1) / rpw;
+  int64_t blocks = std::min<int64_t>((warps_needed + 7) / 8, (int64_t)P.sm_count * occ);
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaMemset(P.dst, 0xff, (size_t)P.N * P.C * 4));
+  for (int i = 0; i < 2; ++i) kern<<<(unsigned)blocks, THREADS>>>(P.rowptr, P.col, P.val, P.src, P.C, P.dst, P.C, P.N, P.C);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  float sum = 0;
+  for (int i = 0; i < reps; ++i) {
+    CK(cudaEventRecord(e0));
+    kern<<<(unsigned)blocks, THREADS>>>(P.rowptr, P.col, P.val, P.src, P.C, P.dst, P.C, P.N, P.C);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    sum += ms;
+  }
+  std::vector<float> a(1 << 16), b(1 << 16);
+  CK(cudaMemcpy(a.data(), P.dst, a.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(b.data(), P.ref, b.size() * 4, cudaMemcpyDeviceToHost));
+  double maxdiff = 0;
+  for (size_t i = 0; i < a.size(); ++i) maxdiff = std::max(maxdiff, (double)fabsf(a[i] - b[i]));
+  const double avg = sum / reps;
+  printf("%-34s regs=%3d occ=%2d blocks=%6lld  avg %.3f ms  %.0f GB/s  frac %.3f  maxdiff %.2e\n", name, fa.numRegs, occ,
+         (long long)blocks, avg, P.bytes / (avg * 1e-3) / 1e9, P.bytes / (avg * 1e-3) / 1e9 / peak, maxdiff);
+  fflush(stdout);
+  return avg;
+}
+
 int main(int argc, char** argv) {
   const int64_t N = argc > 1 ? atoll(argv[1]) : 1000000;
   const int deg = argc > 2 ? atoi(argv[2]) : 32;
@@ -123,8 +162,34 @@ int main(int argc, char** argv) {
   std::vector<V> vs;
 #define ADD(NAME, ...) vs.push_back(V{NAME, [&](bool ref) { return run<__VA_ARGS__>(P, NAME, reps, peak, 0, ref, 1.0f); }, {0, 0, 0}})
   //                                   L   U  THR MINB HINT PF SH
-  if (C <= 64) {
+#define ADDMR(NAME, ...) vs.push_back(V{NAME, [&](bool) { return run_mr<__VA_ARGS__>(P, NAME, reps, peak); }, {0, 0, 0}})
+  //                                  L  GS  U MINB HINT
+  if (C <= 8) {           // feature-sharded multi-GPU slices: 32-byte rows
+    ADD("1row  L2 U2 EL mb6",          2, 2, 256, 6, 3, false);
+    ADDMR("mrow L2 GS4  U2 EL mb6",    2, 4, 2, 6, 3);
+    ADDMR("mrow L2 GS8  U2 EL mb6",    2, 8, 2, 6, 3);
+    ADDMR("mrow L2 GS8  U1 EL mb6",    2, 8, 1, 6, 3);
+    ADDMR("mrow L2 GS16 U2 EL mb6",    2, 16, 2, 6, 3);
+    ADDMR("mrow L2 GS8  U2 ldg mb6",   2, 8, 2, 6, 0);
+    ADDMR("mrow L2 GS8  U2 EL mb8",    2, 8, 2, 8, 3);
+    ADDMR("mrow L2 GS8  U2 EL mb4",    2, 8, 2, 4, 3);
+  } else if (C <= 16) {
+    ADD("1row  L4 U2 EL mb6",          4, 2, 256, 6, 3, false);
+    ADDMR("mrow L4 GS8  U2 EL mb6",    4, 8, 2, 6, 3);
+    ADDMR("mrow L4 GS16 U2 EL mb6",    4, 16, 2, 6, 3);
+    ADDMR("mrow L4 GS16 U4 EL mb6",    4, 16, 4, 6, 3);
+    ADDMR("mrow L4 GS16 U2 ldg mb6",   4, 16, 2, 6, 0);
+    ADDMR("mrow L4 GS16 U2 EL mb8",    4, 16, 2, 8, 3);
+  } else if (C <= 32) {
+    ADD("1row  L8 U2 EL mb8",          8, 2, 256, 8, 3, false);
+    ADD("1row  L8 U4 EL mb6",          8, 4, 256, 6, 3, false);
+    ADDMR("mrow L8 GS16 U2 EL mb6",    8, 16, 2, 6, 3);
+    ADDMR("mrow L8 GS16 U2 EL mb8",    8, 16, 2, 8, 3);
+    ADDMR("mrow L8 GS32 U4 EL mb6",    8, 32, 4, 6, 3);
+    ADDMR("mrow L8 GS16 U2 ldg mb6",   8, 16, 2, 6, 0);
+  } else if (C <= 64) {
     ADD("noalloc PF   mb6",            16, 4, 256, 6, 1, true);
+    ADDMR("mrow L16 GS32 U2 EL mb6",   16, 32, 2, 6, 3);
     ADD("noalloc noPF mb6",            16, 4, 256, 6, 1, false);
     ADD("ldg     noPF mb6",            16, 4, 256, 6, 0, false);
     ADD("ELimm1  PF   mb1(64r)",       16, 4, 256, 1, 3, true);
