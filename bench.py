@@ -302,7 +302,7 @@ def run_gpu_arm(args, w):
         parallelism = "single"
     else:
         from gnn_b200.distributed import PartitionedLSIGF
-        part = PartitionedLSIGF(gso, mode=args.mode, device=dev)
+        part = PartitionedLSIGF(gso, mode=args.mode, device=dev, fused=False if args.no_fused else None)
         if args.mode == "nodes":
             x_local = torch.randn(part.rows_per_rank, B * G, generator=torch.Generator().manual_seed(rank)).to(dev)
         else:
@@ -330,7 +330,7 @@ def run_gpu_arm(args, w):
                       "h2d_bytes_per_step": xh.numel() * 4 * world, "d2h_bytes_per_step": yh.numel() * 4 * world,
                       "ms_per_step": ms_e2e}
         out["clocks"] = clk.summary()
-        parallelism = "%s-partition x%d" % (args.mode, world)
+        parallelism = "%s-partition x%d%s" % (args.mode, world, " (fused hop+NVLink scatter)" if part.fused else "")
 
     if rank == 0:
         line = {
@@ -382,6 +382,7 @@ def main():
     ap.add_argument("--mode", default="features", choices=["nodes", "features"],
                     help="multi-GPU sharding (DESIGN.md §4): feature columns (default) or node rows")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fused", action="store_true", help="multi-GPU: NCCL all-to-all instead of the fused NVLink scatter")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     w = WORKLOADS[args.workload]

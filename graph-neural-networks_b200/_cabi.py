@@ -35,7 +35,15 @@ _SIGNATURES = {
     "b200gf_profile_hops": (c_int, [c_vp, c_int]),
     "b200gf_profile_read": (c_int, [c_vp, ctypes.POINTER(ctypes.c_float), c_int]),
     "b200gf_hop": (c_int, [c_vp, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_int, c_vp]),
-    "b200gf_tap_contract": (c_int, [c_int, c_i64, c_int, c_int, c_int, c_int, PP, ctypes.POINTER(c_i64), c_vp, c_vp,
+    "b200gf_hop_scatter": (c_int, [c_vp, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_int, PP, c_int, c_i64, c_i64, c_i64,
+                                   c_int, c_i64, c_vp]),
+    "b200gf_scatter_rows": (c_int, [c_int, c_vp, c_i64, c_i64, c_int, PP, c_int, c_i64, c_i64, c_i64, c_int, c_i64, c_vp]),
+    "b200gf_symm_alloc": (c_int, [PP, c_sz]),
+    "b200gf_symm_free": (c_int, [c_vp]),
+    "b200gf_symm_export": (c_int, [c_vp, c_vp]),
+    "b200gf_symm_import": (c_int, [c_vp, PP]),
+    "b200gf_symm_close": (c_int, [c_vp]),
+    "b200gf_tap_contract":(c_int, [c_int, c_i64, c_int, c_int, c_int, c_int, PP, ctypes.POINTER(c_i64), c_vp, c_vp,
                                     c_int, c_vp, c_i64, c_int, c_vp, c_sz, c_vp]),
     "b200gf_tap_contract_scratch_bytes": (c_sz, [c_int, c_int, c_int]),
     "b200gf_tap_grad": (c_int, [c_int, c_i64, c_int, c_int, c_int, c_int, c_vp, c_i64, PP, ctypes.POINTER(c_i64),

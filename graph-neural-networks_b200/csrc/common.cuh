@@ -41,9 +41,18 @@ inline int64_t padded_ld(int64_t C, int dtype) {
   return (C + q - 1) / q * q;
 }
 
+// type-erased description of the fused NVLink scatter epilogue (spmm_kernels.cuh: ScatterArgs)
+struct ScatterHost {
+  void* peer[16];
+  int64_t rows_per_peer, out_ld, out_col, stride_b;
+  int gl, n_peers;
+};
+
 // internal launchers (defined across the .cu files) -------------------------------------------------
 int launch_hop(int dtype, int sm_count, const CsrDev& A, int64_t n_rows, const void* src, int64_t src_ld,
-               void* dst, int64_t dst_ld, int C, cudaStream_t st);
+               void* dst, int64_t dst_ld, int C, cudaStream_t st, const ScatterHost* sh = nullptr);
+int launch_scatter_rows(int dtype, const void* src, int64_t src_ld, int64_t n_rows, int C, cudaStream_t st,
+                        const ScatterHost* sh);
 
 struct TermList {            // passed by value to kernels: up to MAX_TERMS (pointer, ld) pairs
   static constexpr int MAX_TERMS = 48;

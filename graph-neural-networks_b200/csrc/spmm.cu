@@ -12,10 +12,23 @@
 //   * U independent LDG.128 per lane are issued before the FMAs (memory-level parallelism);
 //   * col/val of a row are read once, coalesced (lane i holds entry i) and broadcast with SHFL;
 //   * next row's col/val and the row after's rowptr are prefetched while the current row is gathered.
+#include <cstring>
+
 #include "common.cuh"
 #include "spmm_kernels.cuh"
 
 namespace b200gf {
+
+template <typename T>
+static ScatterArgs<T> make_scatter(const ScatterHost* sh) {
+  ScatterArgs<T> sc{};
+  if (sh && sh->n_peers > 0) {
+    for (int i = 0; i < sh->n_peers; ++i) sc.peer[i] = reinterpret_cast<T*>(sh->peer[i]);
+    sc.rows_per_peer = sh->rows_per_peer; sc.out_ld = sh->out_ld; sc.out_col = sh->out_col;
+    sc.stride_b = sh->stride_b; sc.gl = sh->gl; sc.n_peers = sh->n_peers;
+  }
+  return sc;
+}
 
 // Library configuration, chosen from tools/spmm_sweep.cu on B200 (profiles/r1_spmm_sweep.md): 256 threads,
 // registers capped for 6 resident blocks/SM (48 warps: the kernel is latency-bound below that), gathered rows loaded
@@ -23,7 +36,7 @@ namespace b200gf {
 // next-row prefetch (it costs registers and measured slower).
 template <typename T, int VEC, int L, int U>
 static int launch_one(int sm_count, const CsrDev& A, int64_t n_rows, const T* src, int64_t src_ld, T* dst,
-                      int64_t dst_ld, int C, cudaStream_t st) {
+                      int64_t dst_ld, int C, cudaStream_t st, const ScatterHost* sh) {
   constexpr int THREADS = 256, MINB = sizeof(T) == 4 ? 6 : 4, HINT = 3;
   constexpr bool PF = false;
   auto kern = spmm_hop_kernel<T, VEC, L, U, THREADS, MINB, HINT, PF>;
@@ -38,7 +51,7 @@ static int launch_one(int sm_count, const CsrDev& A, int64_t n_rows, const T* sr
   const int64_t cap = (int64_t)sm_count * occ;  // one resident wave: persistent warps stride over the items
   if (blocks > cap) blocks = cap;
   kern<<<(unsigned)blocks, THREADS, 0, st>>>(A.rowptr, A.col, reinterpret_cast<const T*>(A.val), src, src_ld, dst,
-                                             dst_ld, n_rows, C, n_chunks, 1.0f);
+                                             dst_ld, n_rows, C, n_chunks, 1.0f, make_scatter<T>(sh));
   LAUNCH_CHECK();
   return B200GF_OK;
 }
@@ -47,7 +60,7 @@ static int launch_one(int sm_count, const CsrDev& A, int64_t n_rows, const T* sr
 // (profiles/r1_spmm_sweep_smallC.log: C = 8 0.39 -> 0.19 ms, C = 16 0.48 -> 0.34 ms, C = 32 0.75 -> 0.68 ms at N = 1M)
 template <typename T, int VEC, int L, int GS, int U, int MINB>
 static int launch_multirow(int sm_count, const CsrDev& A, int64_t n_rows, const T* src, int64_t src_ld, T* dst,
-                           int64_t dst_ld, int C, cudaStream_t st) {
+                           int64_t dst_ld, int C, cudaStream_t st, const ScatterHost* sh) {
   constexpr int THREADS = 256, HINT = 3;
   auto kern = spmm_hop_multirow_kernel<T, VEC, L, GS, U, THREADS, MINB, HINT>;
   if (n_rows == 0) return B200GF_OK;
@@ -59,37 +72,75 @@ static int launch_multirow(int sm_count, const CsrDev& A, int64_t n_rows, const 
   const int64_t cap = (int64_t)sm_count * occ;
   if (blocks > cap) blocks = cap;
   kern<<<(unsigned)blocks, THREADS, 0, st>>>(A.rowptr, A.col, reinterpret_cast<const T*>(A.val), src, src_ld, dst,
-                                             dst_ld, n_rows, C);
+                                             dst_ld, n_rows, C, make_scatter<T>(sh));
   LAUNCH_CHECK();
   return B200GF_OK;
 }
 
 template <typename T>
 static int launch_typed(int sm_count, const CsrDev& A, int64_t n_rows, const void* src_, int64_t src_ld,
-                        void* dst_, int64_t dst_ld, int C, cudaStream_t st) {
+                        void* dst_, int64_t dst_ld, int C, cudaStream_t st, const ScatterHost* sh) {
   constexpr int VEC = 16 / sizeof(T);
   const T* src = reinterpret_cast<const T*>(src_);
   T* dst = reinterpret_cast<T*>(dst_);
   const int Cv = (C + VEC - 1) / VEC * VEC;
   const bool vec_ok = (src_ld % VEC == 0) && (dst_ld % VEC == 0) && (Cv <= src_ld) && (Cv <= dst_ld) &&
                       ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-  if (!vec_ok) return launch_one<T, 1, 32, 4>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st);
+  if (!vec_ok) {
+    if (sh && sh->n_peers > 0) return B200GF_EUNSUPPORTED;  // the fused scatter needs the 16-byte vector path
+    return launch_one<T, 1, 32, 4>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, nullptr);
+  }
+  if (sh && sh->n_peers > 0 && (sh->gl % VEC != 0 || sh->out_ld % VEC != 0 || sh->out_col % VEC != 0 || sh->stride_b % VEC != 0))
+    return B200GF_EUNSUPPORTED;
   const int nv = Cv / VEC;  // 16-byte vectors per row
   constexpr int MB = sizeof(T) == 4 ? 6 : 4;
-  if (nv <= 1) return launch_multirow<T, VEC, 1, 8, 1, MB>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st);
-  if (nv <= 2) return launch_multirow<T, VEC, 2, 8, 2, MB>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st);
-  if (nv <= 4) return launch_multirow<T, VEC, 4, 16, 2, sizeof(T) == 4 ? 8 : 4>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st);
-  if (nv <= 8) return launch_multirow<T, VEC, 8, 32, 4, MB>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st);
-  if (nv <= 16) return launch_one<T, VEC, 16, 4>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st);
-  return launch_one<T, VEC, 32, 4>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st);
+  if (nv <= 1) return launch_multirow<T, VEC, 1, 8, 1, MB>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);
+  if (nv <= 2) return launch_multirow<T, VEC, 2, 8, 2, MB>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);
+  if (nv <= 4) return launch_multirow<T, VEC, 4, 16, 2, sizeof(T) == 4 ? 8 : 4>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);
+  if (nv <= 8) return launch_multirow<T, VEC, 8, 32, 4, MB>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);
+  if (nv <= 16) return launch_one<T, VEC, 16, 4>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);
+  return launch_one<T, VEC, 32, 4>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);
 }
 
 int launch_hop(int dtype, int sm_count, const CsrDev& A, int64_t n_rows, const void* src, int64_t src_ld,
-               void* dst, int64_t dst_ld, int C, cudaStream_t st) {
+               void* dst, int64_t dst_ld, int C, cudaStream_t st, const ScatterHost* sh) {
   if (C <= 0 || src_ld < C || dst_ld < C) return B200GF_EINVAL;
-  if (dtype == B200GF_F32) return launch_typed<float>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st);
-  if (dtype == B200GF_F64) return launch_typed<double>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st);
+  if (sh && (sh->n_peers < 0 || sh->n_peers > MAX_PEERS)) return B200GF_EINVAL;
+  if (dtype == B200GF_F32) return launch_typed<float>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);
+  if (dtype == B200GF_F64) return launch_typed<double>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);
   return B200GF_EUNSUPPORTED;
+}
+
+// copy-scatter of an existing node-major matrix (the k = 0 term, x itself) into the peers' row-local operands
+template <typename T, int VEC>
+__global__ void scatter_rows_kernel(const T* __restrict__ src, int64_t src_ld, int64_t n_rows, int C,
+                                    const ScatterArgs<T> sc) {
+  const int vpr = C / VEC;
+  const int64_t total = n_rows * vpr;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / vpr;
+    const int cbase = (int)(i - row * vpr) * VEC;
+    const Acc<T, VEC> a = load_vec<T, VEC, 0>(src + row * src_ld + cbase, 0);
+    scatter_store<T, VEC>(sc, row, cbase, a);
+  }
+}
+
+int launch_scatter_rows(int dtype, const void* src, int64_t src_ld, int64_t n_rows, int C, cudaStream_t st,
+                        const ScatterHost* sh) {
+  if (!src || !sh || sh->n_peers <= 0 || sh->n_peers > MAX_PEERS || C <= 0 || src_ld < C) return B200GF_EINVAL;
+  if (n_rows == 0) return B200GF_OK;
+  const int blocks = 148 * 8;
+  if (dtype == B200GF_F32) {
+    if (C % 4 || src_ld % 4 || sh->gl % 4 || sh->out_ld % 4 || sh->out_col % 4 || sh->stride_b % 4) return B200GF_EUNSUPPORTED;
+    scatter_rows_kernel<float, 4><<<blocks, 256, 0, st>>>((const float*)src, src_ld, n_rows, C, make_scatter<float>(sh));
+  } else if (dtype == B200GF_F64) {
+    if (C % 2 || src_ld % 2 || sh->gl % 2 || sh->out_ld % 2 || sh->out_col % 2 || sh->stride_b % 2) return B200GF_EUNSUPPORTED;
+    scatter_rows_kernel<double, 2><<<blocks, 256, 0, st>>>((const double*)src, src_ld, n_rows, C, make_scatter<double>(sh));
+  } else {
+    return B200GF_EUNSUPPORTED;
+  }
+  LAUNCH_CHECK();
+  return B200GF_OK;
 }
 
 }  // namespace b200gf
@@ -101,5 +152,75 @@ extern "C" int b200gf_hop(const b200gf_plan* plan, int e, int direction, const v
   if (direction == B200GF_HOP_BWD && !plan->has_bwd) return B200GF_EINVAL;
   const b200gf::CsrDev& A = direction == B200GF_HOP_FWD ? plan->fwd[e] : plan->bwd[e];
   return b200gf::launch_hop(plan->dtype, plan->sm_count, A, plan->n_rows, src, src_ld, dst, dst_ld, C,
-                            (cudaStream_t)stream);
+                            (cudaStream_t)stream, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fused hop + NVLink scatter, and the symmetric (IPC) buffers it writes into
+// ---------------------------------------------------------------------------------------------------
+static int fill_scatter(b200gf::ScatterHost& sh, const void* const* peers, int n_peers, int64_t rows_per_peer,
+                        int64_t out_ld, int64_t out_col, int gl, int64_t stride_b) {
+  if (!peers || n_peers <= 0 || n_peers > b200gf::MAX_PEERS || rows_per_peer <= 0 || gl <= 0) return B200GF_EINVAL;
+  for (int i = 0; i < n_peers; ++i) {
+    if (!peers[i] || (reinterpret_cast<uintptr_t>(peers[i]) & 15)) return B200GF_EINVAL;
+    sh.peer[i] = const_cast<void*>(peers[i]);
+  }
+  sh.n_peers = n_peers; sh.rows_per_peer = rows_per_peer; sh.out_ld = out_ld; sh.out_col = out_col; sh.gl = gl;
+  sh.stride_b = stride_b;
+  return B200GF_OK;
+}
+
+extern "C" int b200gf_hop_scatter(const b200gf_plan* plan, int e, int direction, const void* src, int64_t src_ld,
+                                  void* dst, int64_t dst_ld, int C, const void* const* peers, int n_peers,
+                                  int64_t rows_per_peer, int64_t out_ld, int64_t out_col, int gl, int64_t stride_b,
+                                  void* stream) {
+  if (!plan || !src || !dst || e < 0 || e >= plan->E) return B200GF_EINVAL;
+  if (direction != B200GF_HOP_FWD && direction != B200GF_HOP_BWD) return B200GF_EINVAL;
+  if (direction == B200GF_HOP_BWD && !plan->has_bwd) return B200GF_EINVAL;
+  b200gf::ScatterHost sh{};
+  int rc = fill_scatter(sh, peers, n_peers, rows_per_peer, out_ld, out_col, gl, stride_b);
+  if (rc) return rc;
+  if (plan->n_rows > rows_per_peer * n_peers || C % gl != 0) return B200GF_EINVAL;
+  const b200gf::CsrDev& A = direction == B200GF_HOP_FWD ? plan->fwd[e] : plan->bwd[e];
+  return b200gf::launch_hop(plan->dtype, plan->sm_count, A, plan->n_rows, src, src_ld, dst, dst_ld, C,
+                            (cudaStream_t)stream, &sh);
+}
+
+extern "C" int b200gf_scatter_rows(int dtype, const void* src, int64_t src_ld, int64_t n_rows, int C,
+                                   const void* const* peers, int n_peers, int64_t rows_per_peer, int64_t out_ld,
+                                   int64_t out_col, int gl, int64_t stride_b, void* stream) {
+  b200gf::ScatterHost sh{};
+  int rc = fill_scatter(sh, peers, n_peers, rows_per_peer, out_ld, out_col, gl, stride_b);
+  if (rc) return rc;
+  if (n_rows > rows_per_peer * n_peers || C % gl != 0) return B200GF_EINVAL;
+  return b200gf::launch_scatter_rows(dtype, src, src_ld, n_rows, C, (cudaStream_t)stream, &sh);
+}
+
+extern "C" int b200gf_symm_alloc(void** ptr, size_t bytes) {
+  if (!ptr || bytes == 0) return B200GF_EINVAL;
+  *ptr = nullptr;
+  if (cudaMalloc(ptr, bytes) != cudaSuccess) { (void)cudaGetLastError(); return B200GF_ENOMEM; }
+  CUDA_TRY(cudaMemset(*ptr, 0, bytes));
+  return B200GF_OK;
+}
+extern "C" int b200gf_symm_free(void* ptr) {
+  if (ptr) CUDA_TRY(cudaFree(ptr));
+  return B200GF_OK;
+}
+extern "C" int b200gf_symm_export(void* ptr, void* handle64) {
+  if (!ptr || !handle64) return B200GF_EINVAL;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  CUDA_TRY(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), ptr));
+  return B200GF_OK;
+}
+extern "C" int b200gf_symm_import(const void* handle64, void** ptr) {
+  if (!ptr || !handle64) return B200GF_EINVAL;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  CUDA_TRY(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return B200GF_OK;
+}
+extern "C" int b200gf_symm_close(void* ptr) {
+  if (ptr) CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+  return B200GF_OK;
 }

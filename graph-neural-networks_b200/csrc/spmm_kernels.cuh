@@ -89,11 +89,38 @@ __device__ __forceinline__ V ld_stream(const V* p) { return __ldcs(p); }
 
 constexpr unsigned FULL = 0xffffffffu;
 
+// Fused hop + collective (feature-sharded multi-GPU path): besides the local result row, each computed row slice is
+// stored straight into the row-local contraction operand of the rank that owns that node row, through NVLink peer
+// pointers (st.global on IPC-mapped memory).  Row r goes to peer r / rows_per_peer, local row r % rows_per_peer;
+// local column (b, g) = b*gl + g lands at b*stride_b + out_col + g.  n_peers == 0 turns it off.
+constexpr int MAX_PEERS = 16;
+template <typename T>
+struct ScatterArgs {
+  T* peer[MAX_PEERS];
+  int64_t rows_per_peer;
+  int64_t out_ld;
+  int64_t out_col;
+  int64_t stride_b;
+  int gl;
+  int n_peers;
+};
+
+template <typename T, int VEC>
+__device__ __forceinline__ void scatter_store(const ScatterArgs<T>& sc, int64_t row, int cbase, const Acc<T, VEC>& acc) {
+  const int64_t q = row / sc.rows_per_peer;
+  const int64_t lr = row - q * sc.rows_per_peer;
+  const int b = cbase / sc.gl;
+  const int g = cbase - b * sc.gl;
+  T* o = sc.peer[q] + lr * sc.out_ld + (int64_t)b * sc.stride_b + sc.out_col + g;
+  store_vec<T, VEC, 0>(o, acc);
+}
+
 template <typename T, int VEC, int L, int U, int THREADS, int MINB, int HINT, bool PF, int SH = 0>
 __global__ void __launch_bounds__(THREADS, MINB)
 spmm_hop_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                 const T* __restrict__ val, const T* __restrict__ src, int64_t src_ld,
-                T* __restrict__ dst, int64_t dst_ld, int64_t n_rows, int C, int n_chunks, float l2_frac) {
+                T* __restrict__ dst, int64_t dst_ld, int64_t n_rows, int C, int n_chunks, float l2_frac,
+                const ScatterArgs<T> sc) {
   uint64_t pol = 0;
   if constexpr (HINT == 2) pol = evict_last_policy(l2_frac);
   if constexpr (HINT == 3) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
@@ -176,7 +203,10 @@ spmm_hop_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ 
 #pragma unroll
       for (int i = 0; i < VEC; ++i) acc.v[i] += __shfl_xor_sync(FULL, acc.v[i], off);
     }
-    if (sub == 0 && col_ok) store_vec<T, VEC, SH>(dst + row * dst_ld + cbase, acc);
+    if (sub == 0 && col_ok) {
+      store_vec<T, VEC, SH>(dst + row * dst_ld + cbase, acc);
+      if (sc.n_peers > 0 && cbase < C) scatter_store<T, VEC>(sc, row, cbase, acc);
+    }
 
     if (!has_next) break;
     item = next;
@@ -200,7 +230,7 @@ template <typename T, int VEC, int L, int GS, int U, int THREADS, int MINB, int 
 __global__ void __launch_bounds__(THREADS, MINB)
 spmm_hop_multirow_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                          const T* __restrict__ val, const T* __restrict__ src, int64_t src_ld,
-                         T* __restrict__ dst, int64_t dst_ld, int64_t n_rows, int C) {
+                         T* __restrict__ dst, int64_t dst_ld, int64_t n_rows, int C, const ScatterArgs<T> sc) {
   static_assert(GS % L == 0 && GS <= 32 && (GS / L) * U <= GS, "bad multirow geometry");
   constexpr int RPW = 32 / GS;
   constexpr int S = GS / L;
@@ -257,7 +287,10 @@ spmm_hop_multirow_kernel(const int64_t* __restrict__ rowptr, const int32_t* __re
 #pragma unroll
       for (int i = 0; i < VEC; ++i) acc.v[i] += __shfl_xor_sync(FULL, acc.v[i], off);
     }
-    if (sub == 0 && col_ok && row_ok) store_vec<T, VEC, 0>(dst + row * dst_ld + cbase, acc);
+    if (sub == 0 && col_ok && row_ok) {
+      store_vec<T, VEC, 0>(dst + row * dst_ld + cbase, acc);
+      if (sc.n_peers > 0) scatter_store<T, VEC>(sc, row, cbase, acc);
+    }
   }
 }
 

@@ -70,6 +70,16 @@ class CudaOps:
         _cabi.check(self.lib.b200gf_hop(plan.handle, e, direction, src.data_ptr(), src.stride(0), dst.data_ptr(),
                                         dst.stride(0), C, self._st()))
 
+    def hop_scatter(self, plan, e, direction, src, dst, C, peers, rows_per_peer, out_ld, out_col, gl, stride_b):
+        _cabi.check(self.lib.b200gf_hop_scatter(plan.handle, e, direction, src.data_ptr(), src.stride(0), dst.data_ptr(),
+                                                dst.stride(0), C, _cabi.ptr_array(peers), len(peers), rows_per_peer,
+                                                out_ld, out_col, gl, stride_b, self._st()))
+
+    def scatter_rows(self, src, n_rows, C, peers, rows_per_peer, out_ld, out_col, gl, stride_b):
+        _cabi.check(self.lib.b200gf_scatter_rows(_ENUM[src.dtype], src.data_ptr(), src.stride(0), n_rows, C,
+                                                 _cabi.ptr_array(peers), len(peers), rows_per_peer, out_ld, out_col, gl,
+                                                 stride_b, self._st()))
+
     def pack_taps(self, h, transpose):
         F, E, K, G = h.shape
         T = 1 + E * (K - 1)
@@ -88,6 +98,66 @@ class CudaOps:
             bias_per_node, out.data_ptr(), out.stride(0), 0, scratch.data_ptr(), sb, self._st()))
 
 
+class _RawMat:
+    """A [rows, ld] device matrix known only by address (memory mapped from a symmetric allocation)."""
+
+    def __init__(self, ptr, ld):
+        self._ptr, self._ld = int(ptr), int(ld)
+
+    def data_ptr(self):
+        return self._ptr
+
+    def stride(self, i):
+        return self._ld if i == 0 else 1
+
+
+class SymmetricOperand:
+    """Double-buffered row-local contraction operand [2][R, row_elems] that every peer can write over NVLink
+    (b200gf_symm_* : cudaMalloc + CUDA IPC).  Double buffering removes the write-after-read hazard between a fast
+    rank's next scatter and a slow rank's current contraction; one tiny all-reduce per call orders the rest."""
+
+    def __init__(self, lib, R, row_elems, dtype, group, device):
+        import ctypes
+        self.lib, self.R, self.row_elems = lib, R, row_elems
+        es = 4 if dtype == torch.float32 else 8
+        self.buf_bytes = R * row_elems * es
+        mine = ctypes.c_void_p()
+        _cabi.check(lib.b200gf_symm_alloc(ctypes.byref(mine), 2 * self.buf_bytes))
+        self.mine = mine.value
+        handle = (ctypes.c_ubyte * 64)()
+        _cabi.check(lib.b200gf_symm_export(ctypes.c_void_p(self.mine), handle))
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        t = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=device)
+        allh = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allh, t, group=group)
+        self.peers, self._opened = [], []
+        for p in range(world):
+            if p == rank:
+                self.peers.append(self.mine)
+                continue
+            raw = (ctypes.c_ubyte * 64)(*allh[p].cpu().tolist())
+            ptr = ctypes.c_void_p()
+            _cabi.check(lib.b200gf_symm_import(raw, ctypes.byref(ptr)))
+            self.peers.append(ptr.value)
+            self._opened.append(ptr.value)
+        self.step = 0
+
+    def peer_ptrs(self, buf):
+        return [p + buf * self.buf_bytes for p in self.peers]
+
+    def local(self, buf):
+        return _RawMat(self.mine + buf * self.buf_bytes, self.row_elems)
+
+    def close(self):
+        import ctypes
+        for p in self._opened:
+            self.lib.b200gf_symm_close(ctypes.c_void_p(p))
+        self._opened = []
+        if self.mine:
+            self.lib.b200gf_symm_free(ctypes.c_void_p(self.mine))
+            self.mine = 0
+
+
 class PartitionedLSIGF:
     """LSIGF forward sharded over the ranks of `group` (see module docstring).
 
@@ -96,9 +166,13 @@ class PartitionedLSIGF:
     In both, row block p covers global nodes [p*rows_per_rank, (p+1)*rows_per_rank) (the last block is zero-padded).
     """
 
-    def __init__(self, gso, mode="nodes", group=None, device=None, ops=None):
+    def __init__(self, gso, mode="nodes", group=None, device=None, ops=None, fused=None):
         assert mode in ("nodes", "features")
         self.mode = mode
+        # fused = hop kernels scatter their rows over NVLink themselves (no NCCL collective on the data path);
+        # default: on whenever the real CUDA ops run under NCCL with <= 16 ranks
+        self._fused_req = fused
+        self._symm = None
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
@@ -122,6 +196,10 @@ class PartitionedLSIGF:
             self.local_nnz = gso.nnz()
             self.plan = self.ops.make_plan_full(gso)
         self._bufs = {}
+        if self._fused_req is None:
+            self.fused = (ops is None and mode == "features" and dist.get_backend(group) == "nccl" and self.world <= 16)
+        else:
+            self.fused = bool(self._fused_req)
 
     # -- helpers -----------------------------------------------------------------------------------
     def feature_slice(self, G):
@@ -187,6 +265,9 @@ class PartitionedLSIGF:
         P = self.world
         if G % P != 0:
             return self._forward_features_rs(h, x_cols, b, B)
+        vec = 4 if self.dtype == torch.float32 else 2
+        if self.fused and (G // P) % vec == 0 and G % vec == 0:
+            return self._forward_features_fused(h, x_cols, b, B)
         Gl = G // P
         Cl = B * Gl
         R = self.rows_per_rank
@@ -217,6 +298,49 @@ class PartitionedLSIGF:
             assert b.shape[1] == 1, "per-node bias is not supported by the partitioned path"
             bias = b.contiguous()
         self.ops.tap_contract([zrow], W, bias, y, R, B, T * G, F)
+        return y[:, :B * F]
+
+    def _forward_features_fused(self, h, x_cols, b, B):
+        """features sharding with the exchange fused into the hop kernel (b200gf_hop_scatter): every computed row slice
+        is stored over NVLink directly into the owning rank's contraction operand [R, B*T*G]; no NCCL collective moves
+        data, one 4-byte all-reduce orders "all scatters done" before the row-local tensor-core contraction."""
+        F, E, K, G = h.shape
+        P = self.world
+        Gl = G // P
+        Cl = B * Gl
+        R = self.rows_per_rank
+        T = 1 + E * (K - 1)
+        row_elems = B * T * G
+        assert x_cols.shape[0] == self.N and x_cols.shape[1] == Cl
+        if self._symm is None or self._symm.row_elems != row_elems:
+            if self._symm is not None:
+                self._symm.close()
+            self._symm = SymmetricOperand(self.ops.lib, R, row_elems, self.dtype, self.group, self.device)
+            self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
+        sy = self._symm
+        buf = sy.step & 1
+        sy.step += 1
+        peers = sy.peer_ptrs(buf)
+        g0 = self.rank * Gl
+        ld = _pad_ld(Cl, self.dtype)
+        z0 = self._buffers(("fz0", Cl), (self.n_pad, ld))
+        z0[:self.N, :Cl].copy_(x_cols)
+        self.ops.scatter_rows(z0, self.N, Cl, peers, R, row_elems, g0, Gl, T * G)
+        for e in range(E):
+            src = z0
+            for k in range(1, K):
+                t = 1 + e * (K - 1) + (k - 1)
+                dst = self._buffers(("fz", e, k, Cl), (self.n_pad, ld))
+                self.ops.hop_scatter(self.plan, e, _cabi.HOP_FWD, src, dst, Cl, peers, R, row_elems, t * G + g0, Gl, T * G)
+                src = dst
+        dist.all_reduce(self._flag, group=self.group)       # every rank's scatters precede its contribution
+        W = self.ops.pack_taps(h, False).reshape(1, T * G, F)
+        y = torch.empty((R, _pad_ld(B * F, self.dtype)), dtype=self.dtype, device=self.device)
+        bias = None
+        if b is not None:
+            assert b.shape[1] == 1, "per-node bias is not supported by the partitioned path"
+            bias = b.contiguous()
+        self.ops.tap_contract([sy.local(buf)], W, bias, y, R, B, T * G, F)
         return y[:, :B * F]
 
     def _forward_features_rs(self, h, x_cols, b, B):

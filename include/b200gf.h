@@ -136,6 +136,30 @@ int b200gf_profile_read(b200gf_plan* plan, float* ms, int n);
 int b200gf_hop(const b200gf_plan* plan, int e, int direction,
                const void* src, int64_t src_ld, void* dst, int64_t dst_ld, int C, void* stream);
 
+/* Fused hop + collective for the feature-sharded multi-GPU path (one compute step followed by an exchange becomes
+ * one kernel): as b200gf_hop, and additionally every computed row slice is stored over NVLink straight into the
+ * row-local contraction operand of the rank that owns the node row.  peers: HOST array of n_peers (<= 16) device
+ * pointers obtained with b200gf_symm_import (peer p's operand, [rows_per_peer, out_ld]); node row r goes to peer
+ * r / rows_per_peer, local row r % rows_per_peer; local column b*gl + g lands at b*stride_b + out_col + g.
+ * Needs the 16-byte vector path (gl, out_ld, out_col, stride_b multiples of 4 floats / 2 doubles).
+ * b200gf_scatter_rows does the same for an existing node-major matrix (the k = 0 term). */
+int b200gf_hop_scatter(const b200gf_plan* plan, int e, int direction,
+                       const void* src, int64_t src_ld, void* dst, int64_t dst_ld, int C,
+                       const void* const* peers, int n_peers, int64_t rows_per_peer,
+                       int64_t out_ld, int64_t out_col, int gl, int64_t stride_b, void* stream);
+int b200gf_scatter_rows(int dtype, const void* src, int64_t src_ld, int64_t n_rows, int C,
+                        const void* const* peers, int n_peers, int64_t rows_per_peer,
+                        int64_t out_ld, int64_t out_col, int gl, int64_t stride_b, void* stream);
+
+/* Symmetric buffers for the above: device memory that other processes of the same node can map (CUDA IPC).
+ * alloc zero-fills; export writes a 64-byte handle to send to the peers (torch.distributed); import maps a peer's
+ * handle and enables peer access; close unmaps. */
+int b200gf_symm_alloc(void** ptr, size_t bytes);
+int b200gf_symm_free(void* ptr);
+int b200gf_symm_export(void* ptr, void* handle64);
+int b200gf_symm_import(const void* handle64, void** ptr);
+int b200gf_symm_close(void* ptr);
+
 /* tap contraction: out[n, b*Q + q] = bias + sum_t sum_p Z_t[n, b*P + p] * W[t][p][q]   for n < n_rows.
  * zs: HOST array of T device pointers (node-major, stride z_ld[t]); W: device [T,P,Q] contiguous;
  * bias NULL / [Q] / [Q, n_rows] (bias_per_node).  accumulate != 0 adds to the existing `out`.

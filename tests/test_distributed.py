@@ -60,7 +60,7 @@ class OracleOps:
         out[:n_rows, :B * Q] = acc.reshape(n_rows, B * Q)
 
 
-def _case(N=203, B=2, G=6, F=5, K=4, E=2, seed=3):
+def _case(N=203, B=2, G=6, F=8, K=4, E=2, seed=3):
     import scipy.sparse as sp
     rng = np.random.default_rng(seed)
     mats = []
@@ -74,7 +74,7 @@ def _case(N=203, B=2, G=6, F=5, K=4, E=2, seed=3):
     return mats, x, h, b
 
 
-def _worker(rank, world, port, backend, mode, dtype_name, result_q):
+def _worker(rank, world, port, backend, mode, dtype_name, result_q, G=6):
     import gnn_b200
     from gnn_b200.distributed import PartitionedLSIGF
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -90,7 +90,7 @@ def _worker(rank, world, port, backend, mode, dtype_name, result_q):
         dist.init_process_group("gloo", rank=rank, world_size=world)
         ops = OracleOps()
     try:
-        mats, x, h, b = _case()
+        mats, x, h, b = _case(G=G)
         B, G, N = x.shape
         F = h.shape[0]
         gso = gnn_b200.SparseGSO.from_scipy(mats, dtype=dtype)
@@ -123,16 +123,17 @@ def _worker(rank, world, port, backend, mode, dtype_name, result_q):
         dist.destroy_process_group()
 
 
-def _run(backend, mode, dtype_name, world=2):
+def _run(backend, mode, dtype_name, world=2, G=6):
     ctx = mp.get_context("spawn")
     q = ctx.SimpleQueue()
-    mp.spawn(_worker, args=(world, _free_port(), backend, mode, dtype_name, q), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), backend, mode, dtype_name, q, G), nprocs=world, join=True)
     return q.get()
 
 
-@pytest.mark.parametrize("mode", ["nodes", "features"])
-def test_partitioned_gloo_world2(mode):
-    err = _run("gloo", mode, "float64")
+@pytest.mark.parametrize("mode,G", [("nodes", 6), ("features", 6), ("features", 5)])
+def test_partitioned_gloo_world2(mode, G):
+    """G = 6: all-to-all exchange of the shifted slices; G = 5 (not divisible by 2): reduce-scatter variant."""
+    err = _run("gloo", mode, "float64", G=G)
     assert err < 1e-12, err
 
 
@@ -150,10 +151,12 @@ def test_row_slice_and_padding():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["nodes", "features"])
+@pytest.mark.parametrize("mode,G", [("nodes", 6), ("features", 6), ("features", 16)])
 @pytest.mark.parametrize("dtype_name,tol", [("float32", 1e-4), ("float64", 1e-11)])
-def test_partitioned_nccl_world2(mode, dtype_name, tol):
+def test_partitioned_nccl_world2(mode, G, dtype_name, tol):
+    """features/G = 6: NCCL all-to-all path; features/G = 16: the fused hop + NVLink scatter kernels (G/P = 8 columns
+    per rank, 16-byte vectors) writing into CUDA-IPC symmetric operands."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    err = _run("nccl", mode, dtype_name)
+    err = _run("nccl", mode, dtype_name, G=G)
     assert err < tol, err

@@ -39,13 +39,13 @@ double run(const Problem& P, const char* name, int reps, double peak, int blocks
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   CK(cudaMemset(P.dst, 0xff, (size_t)P.N * P.C * 4));
   for (int i = 0; i < 2; ++i)
-    kern<<<(unsigned)blocks, THREADS>>>(P.rowptr, P.col, P.val, P.src, P.C, P.dst, P.C, P.N, P.C, n_chunks, frac);
+    kern<<<(unsigned)blocks, THREADS>>>(P.rowptr, P.col, P.val, P.src, P.C, P.dst, P.C, P.N, P.C, n_chunks, frac, ScatterArgs<float>{});
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   float best = 1e30f, sum = 0;
   for (int i = 0; i < reps; ++i) {
     CK(cudaEventRecord(e0));
-    kern<<<(unsigned)blocks, THREADS>>>(P.rowptr, P.col, P.val, P.src, P.C, P.dst, P.C, P.N, P.C, n_chunks, frac);
+    kern<<<(unsigned)blocks, THREADS>>>(P.rowptr, P.col, P.val, P.src, P.C, P.dst, P.C, P.N, P.C, n_chunks, frac, ScatterArgs<float>{});
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -84,13 +84,13 @@ double run_mr(const Problem& P, const char* name, int reps, double peak) {
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   CK(cudaMemset(P.dst, 0xff, (size_t)P.N * P.C * 4));
-  for (int i = 0; i < 2; ++i) kern<<<(unsigned)blocks, THREADS>>>(P.rowptr, P.col, P.val, P.src, P.C, P.dst, P.C, P.N, P.C);
+  for (int i = 0; i < 2; ++i) kern<<<(unsigned)blocks, THREADS>>>(P.rowptr, P.col, P.val, P.src, P.C, P.dst, P.C, P.N, P.C, ScatterArgs<float>{});
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   float sum = 0;
   for (int i = 0; i < reps; ++i) {
     CK(cudaEventRecord(e0));
-    kern<<<(unsigned)blocks, THREADS>>>(P.rowptr, P.col, P.val, P.src, P.C, P.dst, P.C, P.N, P.C);
+    kern<<<(unsigned)blocks, THREADS>>>(P.rowptr, P.col, P.val, P.src, P.C, P.dst, P.C, P.N, P.C, ScatterArgs<float>{});
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
