@@ -7,4 +7,6 @@ from . import _cabi  # noqa: F401
 from .gso import SparseGSO, Plan, plan_for, clear_plan_cache  # noqa: F401
 from .graphML import LSIGF, GraphFilter, install, uninstall, to_node_major, node_major_ld, padded_ld  # noqa: F401
 
-__all__ = ["LSIGF", "GraphFilter", "SparseGSO", "Plan", "plan_for", "install", "uninstall"]
+from .edgevariant import EVGF, EdgeVariantGF  # noqa: F401,E402
+
+__all__ = ["EVGF", "EdgeVariantGF", "LSIGF", "GraphFilter", "SparseGSO", "Plan", "plan_for", "install", "uninstall"]

@@ -234,24 +234,27 @@ _SAVED = {}
 
 
 def install(gml=None):
-    """Point `alegnn.utils.graphML.LSIGF` and `.GraphFilter` at this module.
+    """Point `alegnn.utils.graphML.LSIGF`, `.GraphFilter`, `.EVGF` and `.EdgeVariantGF` at this package.
 
     `GraphFilter.forward` in the reference looks `LSIGF` up as a module global at call time (graphML.py:2137), so
     this also accelerates its hybrid EdgeVariantGF (:2686), jARMA (:592) and GatedGRNN (:1403,:1461) call sites.
-    Architectures built AFTER install() get this module's GraphFilter (plan cached in addGSO).
+    Architectures built AFTER install() get this package's layers (plan cached in addGSO).
     """
+    from . import edgevariant
     if gml is None:
         import alegnn.utils.graphML as gml
     if id(gml) not in _SAVED:
-        _SAVED[id(gml)] = (gml, gml.LSIGF, gml.GraphFilter)
+        _SAVED[id(gml)] = (gml, {n: getattr(gml, n) for n in ("LSIGF", "GraphFilter", "EVGF", "EdgeVariantGF")})
     gml.LSIGF = LSIGF
     gml.GraphFilter = GraphFilter
+    gml.EVGF = edgevariant.EVGF
+    gml.EdgeVariantGF = edgevariant.EdgeVariantGF
     return gml
 
 
 def uninstall(gml=None):
-    for key, (mod, lsigf, gf) in list(_SAVED.items()):
+    for key, (mod, saved) in list(_SAVED.items()):
         if gml is None or mod is gml:
-            mod.LSIGF = lsigf
-            mod.GraphFilter = gf
+            for name, obj in saved.items():
+                setattr(mod, name, obj)
             del _SAVED[key]

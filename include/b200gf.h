@@ -180,6 +180,26 @@ int b200gf_tap_grad(int dtype, int64_t n_rows, int B, int P, int Q, int T,
                     void* dW, void* scratch, size_t scratch_bytes, void* stream);
 size_t b200gf_tap_grad_scratch_bytes(int dtype, int64_t n_rows, int B, int P, int Q, int T);
 
+/* ------------------------------------------------------------------------------------------------
+ * Edge-variant graph filter, the variant of the path used by EdgeVariantGF (config "EdgeNet"):
+ *   EVGF(S, x, b)   alegnn/utils/graphML.py:389-488,   EdgeVariantGF.forward  :2670-2698
+ * One call per edge feature e, on a compact node set of NA nodes (the rows/columns of Phi that are not identically
+ * zero).  Pattern: CSR (rowptr [NA+1], col [nnz]) shared by all (f, k, g).  w [F, K, G, nnz] = Phi^(k)_{f e g} on the
+ * pattern (COLUMN convention u_k = Phi^(k) u_{k-1}, u_{-1} = x_g).  xA [B, G, NA].
+ * forward : states [K, F*G*B, NA] (kept for backward), S [F, G, B, NA] = sum_k u_k (caller sums over g, e; adds bias)
+ * backward: dyA [B, F, NA] -> dw [F, K, G, nnz], dxA [B, G, NA]; needs rowidx [nnz] (row of each non-zero), the
+ *           transposed pattern (rowptrT, colT) with perm[it] = index of that entry in the forward pattern, and
+ *           lam = scratch of 2 * F*G*B*NA elements.
+ * ---------------------------------------------------------------------------------------------- */
+int b200gf_ev_forward(int dtype, int64_t NA, int B, int G, int F, int K,
+                      const int64_t* rowptr, const int32_t* col, int64_t nnz,
+                      const void* w, const void* xA, void* states, void* S, void* stream);
+int b200gf_ev_backward(int dtype, int64_t NA, int B, int G, int F, int K,
+                       const int32_t* rowidx, const int32_t* col,
+                       const int64_t* rowptrT, const int32_t* colT, const int64_t* perm, int64_t nnz,
+                       const void* w, const void* xA, const void* states, const void* dyA,
+                       void* lam, void* dw, void* dxA, void* stream);
+
 /* layout conversion between the reference's [C, N] (feature-major, C = B*G) and node-major [N, ld] */
 int b200gf_to_node_major(int dtype, const void* src_cn, void* dst_nc, int64_t dst_ld,
                          int64_t N, int C, void* stream);

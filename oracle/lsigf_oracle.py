@@ -227,3 +227,51 @@ def random_case(seed, N, B, G, F, K, E=1, avg_deg=6, bias="F1", symmetric=False)
         b = None
     dy = rng.standard_normal((B, F, N))
     return dict(h=h, S=S, x=x, b=b, dy=dy)
+
+
+# --------------------------------------------------------------------------------------------
+# edge-variant filter (variant row a-7)
+# --------------------------------------------------------------------------------------------
+def evgf_dense(Phi, x, b=None):
+    """EVGF(S, x, b) — graphML.py:389-488.  Phi [F,E,K,G,N,N], x [B,G,N].  Column convention (graphML.py:464,475):
+    u_0 = Phi^(0) x_g, u_k = Phi^(k) u_{k-1};  y_f = sum_{e,k,g} u_k + b_f."""
+    Phi = np.asarray(Phi)
+    x = np.asarray(x)
+    F, E, K, G, N, _ = Phi.shape
+    u = np.einsum("fegij,bgj->bfegi", Phi[:, :, 0], x)
+    y = u.sum(axis=(2, 3))
+    for k in range(1, K):
+        u = np.einsum("fegij,bfegj->bfegi", Phi[:, :, k], u)
+        y = y + u.sum(axis=(2, 3))
+    if b is not None:
+        y = y + np.asarray(b)[None]
+    return y
+
+
+def edge_variant_masks(S, M, K, tol=1e-9):
+    """sparsityPatternFull of EdgeVariantGF.addGSO (graphML.py:2608-2668): [1,E,K,1,N,N]; k = 0 is the identity on the
+    first M nodes, k >= 1 the pattern of |S|+I, both restricted to entries with i < M or j < M when M < N."""
+    S = np.asarray(S)
+    E, N, _ = S.shape
+    eye = np.eye(N)[None].repeat(E, axis=0)
+    pattern = ((np.abs(S) + eye) > tol).astype(S.dtype)
+    if M < N:
+        idx = np.arange(N)
+        hybrid = ((idx[:, None] < M) | (idx[None, :] < M)).astype(S.dtype)
+    else:
+        hybrid = np.ones((N, N), dtype=S.dtype)
+    pattern = pattern * hybrid[None]
+    ident = eye * hybrid[None]
+    full = np.concatenate([ident[:, None]] + [pattern[:, None]] * (K - 1), axis=1)  # [E,K,N,N]
+    return full[None, :, :, None]
+
+
+def edge_variant_gf_forward(weightEV, weightLSI, bias, S, M, x):
+    """EdgeVariantGF.forward — graphML.py:2670-2698 (bias enters twice in the hybrid case, as in the reference)."""
+    K = weightEV.shape[2]
+    N = S.shape[1]
+    Phi = np.asarray(weightEV) * edge_variant_masks(S, M, K)
+    y = evgf_dense(Phi, x, bias)
+    if M < N:
+        y = y + lsigf_dense(weightLSI, S, x, bias)
+    return y

@@ -131,9 +131,55 @@ def gen_selectiongnn_cfg1(gml):
     print("selectiongnn_cfg1.npz: keys", sorted(out.keys()))
 
 
+def gen_evgf(gml):
+    """EVGF (graphML.py:389-488) and EdgeVariantGF (graphML.py:2511-2712), full (M = N) and hybrid (M < N), fp64."""
+    out = {}
+    # (a) the functional on arbitrary masked filter matrices
+    rng = np.random.default_rng(301)
+    F, E, K, G, N, B = 3, 2, 3, 2, 10, 2
+    mask = (rng.random((1, E, 1, 1, N, N)) < 0.3) | np.eye(N, dtype=bool)[None, None, None, None]
+    Phi = rng.standard_normal((F, E, K, G, N, N)) * mask
+    x = rng.standard_normal((B, G, N))
+    b = rng.standard_normal((F, 1))
+    Pt = torch.tensor(Phi, requires_grad=True)
+    xt = torch.tensor(x, requires_grad=True)
+    bt = torch.tensor(b, requires_grad=True)
+    y = gml.EVGF(Pt, xt, bt)
+    dy = rng.standard_normal(tuple(y.shape))
+    y.backward(torch.tensor(dy))
+    out.update({"f_Phi": Phi, "f_x": x, "f_b": b, "f_dy": dy, "f_y": y.detach().numpy(),
+                "f_dPhi": Pt.grad.numpy() * mask, "f_dx": xt.grad.numpy(), "f_db": bt.grad.numpy()})
+    # (b) the layer: full and hybrid
+    for tag, (N, M, E, K, G, F, B, Nin) in {"full": (9, 9, 1, 3, 2, 3, 2, 9), "hyb": (12, 5, 2, 3, 3, 2, 3, 10)}.items():
+        rng = np.random.default_rng(310 + N)
+        S = orc.random_sparse_gso(rng, N, 3, E)
+        torch.manual_seed(N)
+        layer = gml.EdgeVariantGF(G, F, K, M, N, E, True).double()
+        with torch.no_grad():  # larger weights than the 1/sqrt(GKN) init so that the comparison is not all bias
+            layer.weightEV.mul_(5.0)
+        layer.addGSO(torch.tensor(S))
+        x = rng.standard_normal((B, G, Nin))
+        xt = torch.tensor(x, requires_grad=True)
+        y = layer(xt)
+        dy = rng.standard_normal(tuple(y.shape))
+        y.backward(torch.tensor(dy))
+        out[tag + "_meta"] = np.array([N, M, E, K, G, F, B, Nin])
+        out[tag + "_S"] = S
+        out[tag + "_x"] = x
+        out[tag + "_dy"] = dy
+        out[tag + "_y"] = y.detach().numpy()
+        out[tag + "_dx"] = xt.grad.numpy()
+        for name, p in layer.named_parameters():
+            out[tag + "_p_" + name] = p.detach().numpy()
+            out[tag + "_g_" + name] = p.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "evgf_cases.npz"), **out)
+    print("evgf_cases.npz:", sorted(k for k in out if k.endswith("_y")))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gml = ref_import.import_reference()
     gen_lsigf(gml)
     gen_graphfilter(gml)
     gen_selectiongnn_cfg1(gml)
+    gen_evgf(gml)
