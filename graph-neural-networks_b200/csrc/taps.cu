@@ -180,8 +180,8 @@ static TapGradGeom tap_grad_geom(int64_t n_rows, int B, int P, int Q, int T) {
   g.p_tiles = (P + TG_BP - 1) / TG_BP;
   g.q_tiles = (Q + TG_BQ - 1) / TG_BQ;
   const int64_t R = n_rows * B;
-  const int64_t per = (int64_t)T * g.p_tiles * g.q_tiles;
-  int64_t want = (148 * 4 + per - 1) / per;  // aim at ~4 blocks per SM in total
+  const int64_t per = (int64_t)((T + 4) / 5) * g.p_tiles * g.q_tiles;  // the FP32 fast path groups 5 terms per block
+  int64_t want = (148 * 2 + per - 1) / per;  // aim at ~2 resident blocks per SM in total
   if (want < 1) want = 1;
   int64_t rpc = (R + want - 1) / want;
   if (rpc < 256) rpc = 256;
@@ -261,6 +261,116 @@ tap_grad_partial_kernel(const T* __restrict__ A, int64_t a_ld, TermList vs, int6
   }
 }
 
+// FP32 fast path: one block = TPB terms x 64 threads, every thread an 8 x 8 micro-tile of its term's 64 x 64 output
+// tile; the A tile is staged once per row step and shared by all TPB terms (4 LDS.128 per 64 FMAs).
+// Needs 16-byte aligned rows (P, Q, a_ld, v_ld multiples of 4).  Same partial layout as the generic kernel.
+template <int TPB>
+__global__ void __launch_bounds__(64 * TPB, 1)
+tap_grad_multi_kernel(const float* __restrict__ A, int64_t a_ld, TermList vs, int t_base, int64_t n_rows, int B, int P,
+                      int Q, int64_t rows_per_chunk, int q_tiles, float* __restrict__ partial, int T_terms) {
+  constexpr int BK = 16;
+  constexpr int NT = 64 * TPB;
+  constexpr int NV = (1 + TPB) * BK * 16;          // float4 per stage
+  constexpr int PER = (NV + NT - 1) / NT;          // float4 per thread per stage
+  __shared__ __align__(16) float As[2][BK][64];    // double-buffered: global loads of step s+1 overlap the FMAs of step s
+  __shared__ __align__(16) float Vs[2][TPB][BK][64];
+  const int chunk = blockIdx.x;
+  const int p0 = (blockIdx.z / q_tiles) * 64, q0 = (blockIdx.z % q_tiles) * 64;
+  const int64_t R = n_rows * B;
+  const int64_t rbeg = (int64_t)chunk * rows_per_chunk;
+  const int64_t rend = min(R, rbeg + rows_per_chunk);
+  const int tid = threadIdx.x;
+  const int tt = tid / 64, l64 = tid % 64;
+  const int ty = l64 / 8, tx = l64 % 8;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  float4 stage[PER];
+  auto fetch = [&](int64_t r0) {
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int idx = tid + u * NT;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < NV) {
+        const int m = idx / (BK * 16);
+        const int rem = idx - m * (BK * 16);
+        const int kk = rem / 16, c4 = (rem % 16) * 4;
+        const int64_t r = r0 + kk;
+        if (r < rend) {
+          const int64_t n = r / B;
+          const int b = (int)(r - n * B);
+          if (m == 0) {
+            if (p0 + c4 < P) v = __ldg(reinterpret_cast<const float4*>(A + n * a_ld + (int64_t)b * P + p0 + c4));
+          } else {
+            const float* V = reinterpret_cast<const float*>(vs.ptr[t_base + m - 1]);
+            if (q0 + c4 < Q) v = __ldg(reinterpret_cast<const float4*>(V + n * vs.ld[t_base + m - 1] + (int64_t)b * Q + q0 + c4));
+          }
+        }
+      }
+      stage[u] = v;
+    }
+  };
+  auto commit = [&](int buf) {
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int idx = tid + u * NT;
+      if (idx < NV) {
+        const int m = idx / (BK * 16);
+        const int rem = idx - m * (BK * 16);
+        const int kk = rem / 16, c4 = (rem % 16) * 4;
+        if (m == 0) *reinterpret_cast<float4*>(&As[buf][kk][c4]) = stage[u];
+        else *reinterpret_cast<float4*>(&Vs[buf][m - 1][kk][c4]) = stage[u];
+      }
+    }
+  };
+
+  if (rbeg < rend) {
+    fetch(rbeg);
+    commit(0);
+  }
+  __syncthreads();
+  int buf = 0;
+  for (int64_t r0 = rbeg; r0 < rend; r0 += BK) {
+    const bool more = r0 + BK < rend;
+    if (more) fetch(r0 + BK);                       // in flight while this step computes
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[8], v[8];
+      *reinterpret_cast<float4*>(&a[0]) = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8]);
+      *reinterpret_cast<float4*>(&a[4]) = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8 + 4]);
+      *reinterpret_cast<float4*>(&v[0]) = *reinterpret_cast<const float4*>(&Vs[buf][tt][kk][tx * 8]);
+      *reinterpret_cast<float4*>(&v[4]) = *reinterpret_cast<const float4*>(&Vs[buf][tt][kk][tx * 8 + 4]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], v[j], acc[i][j]);
+    }
+    if (more) commit(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+  float* __restrict__ o = partial + ((int64_t)chunk * T_terms + t_base + tt) * P * Q;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int p = p0 + ty * 8 + i;
+    if (p >= P) continue;
+#pragma unroll
+    for (int j = 0; j < 8; j += 4) {
+      const int q = q0 + tx * 8 + j;
+      if (q < Q) *reinterpret_cast<float4*>(o + (int64_t)p * Q + q) = make_float4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
+    }
+  }
+}
+
+template <int TPB>
+static void launch_tap_grad_multi(dim3 grid, cudaStream_t st, const float* A, int64_t a_ld, const TermList& tl, int t_base,
+                                  int64_t n_rows, int B, int P, int Q, int64_t rpc, int q_tiles, float* partial, int T) {
+  tap_grad_multi_kernel<TPB><<<grid, 64 * TPB, 0, st>>>(A, a_ld, tl, t_base, n_rows, B, P, Q, rpc, q_tiles, partial, T);
+}
+
 // second pass: fixed-order sum over chunks; out_mode 1 scatters into the taps layout dh[F=Q,E,K,G=P]
 template <typename T>
 __global__ void tap_grad_reduce_kernel(const T* __restrict__ partial, int n_chunks, int T_terms, int P, int Q,
@@ -305,6 +415,26 @@ int launch_tap_grad(int dtype, int64_t n_rows, int B, int P, int Q, int T, const
     dim3 grid((unsigned)g.n_chunks, (unsigned)tn, (unsigned)(g.p_tiles * g.q_tiles));
     // partial layout is [chunk][T][P][Q] over ALL T terms; offset the base so block t writes term t0 + t
     char* part = (char*)scratch + (size_t)t0 * P * Q * es;
+    bool fast = dtype == B200GF_F32 && P % 4 == 0 && Q % 4 == 0 && a_ld % 4 == 0 && ((uintptr_t)A & 15) == 0;
+    for (int i = 0; i < tn && fast; ++i) fast = tl.ld[i] % 4 == 0 && ((uintptr_t)tl.ptr[i] & 15) == 0;
+    if (fast) {
+      // terms in groups of up to 5 sharing the staged A tile
+      for (int tb = 0; tb < tn; tb += 5) {
+        const int tpb = min(5, tn - tb);
+        dim3 g2((unsigned)g.n_chunks, 1, (unsigned)(g.p_tiles * g.q_tiles));
+        const float* Af = (const float*)A;
+        float* pf = (float*)part;
+        switch (tpb) {
+          case 1: launch_tap_grad_multi<1>(g2, st, Af, a_ld, tl, tb, n_rows, B, P, Q, g.rows_per_chunk, g.q_tiles, pf, T); break;
+          case 2: launch_tap_grad_multi<2>(g2, st, Af, a_ld, tl, tb, n_rows, B, P, Q, g.rows_per_chunk, g.q_tiles, pf, T); break;
+          case 3: launch_tap_grad_multi<3>(g2, st, Af, a_ld, tl, tb, n_rows, B, P, Q, g.rows_per_chunk, g.q_tiles, pf, T); break;
+          case 4: launch_tap_grad_multi<4>(g2, st, Af, a_ld, tl, tb, n_rows, B, P, Q, g.rows_per_chunk, g.q_tiles, pf, T); break;
+          default: launch_tap_grad_multi<5>(g2, st, Af, a_ld, tl, tb, n_rows, B, P, Q, g.rows_per_chunk, g.q_tiles, pf, T); break;
+        }
+        LAUNCH_CHECK();
+      }
+      continue;
+    }
     if (dtype == B200GF_F32)
       tap_grad_partial_kernel<float><<<grid, 256, 0, st>>>((const float*)A, a_ld, tl, n_rows, B, P, Q,
                                                            g.rows_per_chunk, g.q_tiles, (float*)part, T);
@@ -361,6 +491,40 @@ bias_grad_partial_kernel(const T* __restrict__ dy, int64_t dy_ld, int64_t n_rows
   }
 }
 
+// FP32 fast path for compact rows (dy_ld == B*F) with (4*256) % F == 0: the chunk is one contiguous float4 stream and a
+// thread always sees the same 4 columns, so it accumulates them in registers (4 loads in flight), then threads with the
+// same column group are summed in a fixed order through shared memory.
+__global__ void __launch_bounds__(256)
+bias_grad_partial_vec_kernel(const float* __restrict__ dy, int64_t n_rows, int B, int F, float* __restrict__ partial) {
+  __shared__ float4 red[256];
+  const int64_t n0 = (int64_t)blockIdx.x * BG_ROWS;
+  const int64_t n1 = min(n_rows, n0 + BG_ROWS);
+  const int64_t nvec = (n1 - n0) * B * F / 4;
+  const float4* __restrict__ base = reinterpret_cast<const float4*>(dy + n0 * B * F);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int64_t i = threadIdx.x;
+  for (; i + 3 * 256 < nvec; i += 4 * 256) {
+    const float4 a = __ldg(base + i), b = __ldg(base + i + 256), c = __ldg(base + i + 512), d = __ldg(base + i + 768);
+    acc.x += (a.x + b.x) + (c.x + d.x); acc.y += (a.y + b.y) + (c.y + d.y);
+    acc.z += (a.z + b.z) + (c.z + d.z); acc.w += (a.w + b.w) + (c.w + d.w);
+  }
+  for (; i < nvec; i += 256) {
+    const float4 a = __ldg(base + i);
+    acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  const int groups = F / 4;  // threads tid, tid + groups, tid + 2*groups, ... hold the same columns
+  if (threadIdx.x < groups) {
+    float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = threadIdx.x; t < 256; t += groups) {
+      tot.x += red[t].x; tot.y += red[t].y; tot.z += red[t].z; tot.w += red[t].w;
+    }
+    float* o = partial + (int64_t)blockIdx.x * F + threadIdx.x * 4;
+    o[0] = tot.x; o[1] = tot.y; o[2] = tot.z; o[3] = tot.w;
+  }
+}
+
 template <typename T>
 __global__ void bias_grad_reduce_kernel(const T* __restrict__ partial, int n_chunks, int F, T* __restrict__ db) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
@@ -402,7 +566,10 @@ int launch_bias_grad(int dtype, int64_t n_rows, int B, int F, const void* dy, in
   if (!scratch || scratch_bytes < bias_grad_scratch_bytes(dtype, n_rows, B, F)) return B200GF_EWORKSPACE;
   const int n_chunks = (int)((n_rows + BG_ROWS - 1) / BG_ROWS);
   if (dtype == B200GF_F32) {
-    if (n_chunks > 0)
+    const bool vec = F % 4 == 0 && 1024 % F == 0 && dy_ld == (int64_t)B * F && ((uintptr_t)dy & 15) == 0;
+    if (n_chunks > 0 && vec)
+      bias_grad_partial_vec_kernel<<<n_chunks, 256, 0, st>>>((const float*)dy, n_rows, B, F, (float*)scratch);
+    else if (n_chunks > 0)
       bias_grad_partial_kernel<float><<<n_chunks, 256, 0, st>>>((const float*)dy, dy_ld, n_rows, B, F, (float*)scratch);
     bias_grad_reduce_kernel<float><<<(F + 127) / 128, 128, 0, st>>>((const float*)scratch, n_chunks, F, (float*)dbias);
   } else {

@@ -83,6 +83,7 @@ class _LSIGFFunction(torch.autograd.Function):
         B, _, N = x.shape
         dt = x.dtype
         hc = h.contiguous()
+        ctx.x_node_major = node_major_ld(x) is not None
         xn, x_ld = to_node_major(x)
         bias_per_node = 0
         bc = None
@@ -130,7 +131,16 @@ class _LSIGFFunction(torch.autograd.Function):
                                  dh.data_ptr(), None if db is None else db.data_ptr(), ctx.bias_per_node,
                                  ws.data_ptr(), ws_bytes, B, G, F_, K, _stream())
         _cabi.check(rc)
-        dx = _as_bcn_view(dxbuf, B, G, N) if need_dx else None
+        dx = None
+        if need_dx:
+            if ctx.x_node_major:
+                dx = _as_bcn_view(dxbuf, B, G, N)       # the producer of x reads it through the same strides
+            else:
+                # x was a plain [B, G, N] tensor: hand back a contiguous gradient (one coalesced tiled transpose)
+                # instead of a strided view that autograd would re-copy element-wise (measured 1.1 ms vs 0.1 ms)
+                dx = torch.empty((B, G, N), dtype=dt, device=dy.device)
+                _cabi.check(lib.b200gf_to_feature_major(_ENUM[dt], dxbuf.data_ptr(), ldc, dx.data_ptr(), N, B * G,
+                                                        _stream()))
         return (dh if need_dh else None), dx, db, None
 
 
