@@ -38,18 +38,26 @@ WORKLOADS = {
     "cfg3": dict(graph="knn", N=1682, deg=10, E=1, K=5, G=64, F=64, B=32, seed=3),
     "cfg4": dict(graph="er", N=200_000, deg=16, E=4, K=3, G=32, F=32, B=32, seed=4),
     "tiny": dict(graph="er", N=20_000, deg=16, E=1, K=5, G=64, F=64, B=1, seed=9),
+    # stochastic block model, 1000 communities of 1000 nodes, ~80 % of the edges inside a community (avgDeg ~ 32);
+    # nodes are numbered community by community, so gathers have the locality a real graph ordering would give
+    "sbm1m": dict(graph="sbm", N=1_000_000, deg=32, E=1, K=5, G=64, F=64, B=1, seed=6, communities=1000, intra=0.8),
 }
 
 
 def describe(w):
     return "%s N=%d avgDeg=%d E=%d K=%d G=%d F=%d B=%d fp32" % (
-        {"er": "Erdos-Renyi", "knn": "kNN-like"}[w["graph"]], w["N"], w["deg"], w["E"], w["K"], w["G"], w["F"], w["B"])
+        {"er": "Erdos-Renyi", "knn": "kNN-like", "sbm": "SBM(%d communities)" % w.get("communities", 0)}[w["graph"]], w["N"], w["deg"], w["E"], w["K"], w["G"], w["F"], w["B"])
 
 
 def make_gso(w):
     from gnn_b200 import graphs
     if w["graph"] == "er":
         return graphs.er_gso(w["N"], w["deg"], seed=w["seed"], E=w["E"])
+    if w["graph"] == "sbm":
+        C, n = w["communities"], w["N"] // w["communities"]
+        p_in = w["deg"] * w["intra"] / (n - 1)
+        p_out = w["deg"] * (1 - w["intra"]) / (w["N"] - n)
+        return graphs.sbm_gso(w["N"], C, p_in, p_out, seed=w["seed"], E=w["E"])
     return graphs.knn_like_gso(w["N"], w["deg"], seed=w["seed"])
 
 
@@ -155,7 +163,7 @@ def cpu_dense_sample(w, n_dense, reps):
     from gnn_b200 import graphs
     torch.set_num_threads(os.cpu_count() or 1)
     ww = dict(w, N=n_dense)
-    gso = graphs.er_gso(n_dense, w["deg"], seed=w["seed"], E=w["E"]) if w["graph"] == "er" else \
+    gso = graphs.er_gso(n_dense, w["deg"], seed=w["seed"], E=w["E"]) if w["graph"] != "knn" else \
         graphs.knn_like_gso(n_dense, w["deg"], seed=w["seed"])
     S = gso.to_dense().float()
     g = torch.Generator().manual_seed(0)
@@ -220,6 +228,7 @@ def run_gpu_arm(args, w):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("B200GF_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = _cabi.load()
     E, K, G, F, B, N = w["E"], w["K"], w["G"], w["F"], w["B"], w["N"]
@@ -309,8 +318,13 @@ def run_gpu_arm(args, w):
             g0, g1 = part.feature_slice(G)
             x_local = torch.randn(N, B * (g1 - g0), generator=torch.Generator().manual_seed(rank)).to(dev)
         fwd = lambda: part.forward(h, x_local, b, B=B)          # noqa: E731
+        hops = E * (K - 1)
+        cap = hops * (args.steps + args.warmup)
+        lib.b200gf_profile_hops(part.plan.handle, cap)
         with torch.no_grad(), ClockSampler(local) as clk:
             ms = timed(fwd, args.steps, args.warmup)
+        hop_ms = ctypes_floats(lib, part.plan, cap)[hops * args.warmup:]
+        lib.b200gf_profile_hops(part.plan.handle, 0)
         # e2e: every rank copies its shard in from pinned host memory and its result rows back
         xh = x_local.cpu().pin_memory()
         yh = torch.empty(part.rows_per_rank, B * F).pin_memory()
@@ -321,11 +335,21 @@ def run_gpu_arm(args, w):
 
         with torch.no_grad():
             ms_e2e = timed(e2e_step, max(3, args.steps // 2), 2)
+        # my kernels per rank and step: pack_taps, split_w, tc_contract, the hops, and the scatter of the k = 0 slice
+        launches_per_step = (E * (K - 1) + 3 + (1 if part.fused else 0)) * world
         if args.mode == "nodes":
-            launches_per_step = 1 + E * (K - 1) + 1
+            c_loc, nnz_loc, rows_loc = B * G, part.local_nnz // E, part.rows_per_rank
         else:
-            launches_per_step = 1 + E * (K - 1) + 1
-        out["roofline"] = None
+            g0, g1 = part.feature_slice(G)
+            c_loc, nnz_loc, rows_loc = B * (g1 - g0), nnz_e, N
+        hop_bytes = hop_algorithmic_bytes(nnz_loc, rows_loc, c_loc)
+        hop_avg_ms = float(np.mean(hop_ms)) if len(hop_ms) else float("nan")
+        achieved = hop_bytes / (hop_avg_ms * 1e-3) / 1e9
+        out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                           "traffic": None, "kernel": "spmm_hop_kernel (rank 0 shard: %d rows x %d columns, %d nnz)" %
+                                                        (rows_loc, c_loc, nnz_loc),
+                           "bytes_per_launch": hop_bytes, "ms_per_launch": hop_avg_ms, "launches_timed": len(hop_ms),
+                           "peak_source": peak_src, "kernel_share_of_step": float(np.sum(hop_ms)) / (ms * args.steps)}
         out["e2e"] = {"value": ops_per_step / (ms_e2e * 1e-3), "unit": "edge-feature-op/s",
                       "h2d_bytes_per_step": xh.numel() * 4 * world, "d2h_bytes_per_step": yh.numel() * 4 * world,
                       "ms_per_step": ms_e2e}

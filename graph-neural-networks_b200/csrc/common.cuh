@@ -111,5 +111,5 @@ struct b200gf_plan {
 namespace b200gf {
 // hop launch of forward/backward, bracketed with events when profiling is on
 int plan_hop(const b200gf_plan* p, const CsrDev& A, const void* src, int64_t src_ld, void* dst, int64_t dst_ld, int C,
-             cudaStream_t st);
+             cudaStream_t st, const ScatterHost* sh = nullptr);
 }

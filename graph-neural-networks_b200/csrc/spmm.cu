@@ -151,8 +151,7 @@ extern "C" int b200gf_hop(const b200gf_plan* plan, int e, int direction, const v
   if (direction != B200GF_HOP_FWD && direction != B200GF_HOP_BWD) return B200GF_EINVAL;
   if (direction == B200GF_HOP_BWD && !plan->has_bwd) return B200GF_EINVAL;
   const b200gf::CsrDev& A = direction == B200GF_HOP_FWD ? plan->fwd[e] : plan->bwd[e];
-  return b200gf::launch_hop(plan->dtype, plan->sm_count, A, plan->n_rows, src, src_ld, dst, dst_ld, C,
-                            (cudaStream_t)stream, nullptr);
+  return b200gf::plan_hop(plan, A, src, src_ld, dst, dst_ld, C, (cudaStream_t)stream, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -182,8 +181,7 @@ extern "C" int b200gf_hop_scatter(const b200gf_plan* plan, int e, int direction,
   if (rc) return rc;
   if (plan->n_rows > rows_per_peer * n_peers || C % gl != 0) return B200GF_EINVAL;
   const b200gf::CsrDev& A = direction == B200GF_HOP_FWD ? plan->fwd[e] : plan->bwd[e];
-  return b200gf::launch_hop(plan->dtype, plan->sm_count, A, plan->n_rows, src, src_ld, dst, dst_ld, C,
-                            (cudaStream_t)stream, &sh);
+  return b200gf::plan_hop(plan, A, src, src_ld, dst, dst_ld, C, (cudaStream_t)stream, &sh);
 }
 
 extern "C" int b200gf_scatter_rows(int dtype, const void* src, int64_t src_ld, int64_t n_rows, int C,

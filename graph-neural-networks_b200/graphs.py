@@ -78,22 +78,28 @@ def er_gso(N, avg_deg, seed=0, E=1, dtype=torch.float32):
 
 
 def sbm_gso(N, n_communities, p_intra, p_inter, seed=0, E=1, dtype=torch.float32):
+    """Stochastic block model with (near-)equal communities of consecutive node ids.  Vectorised sampling: per
+    community a Binomial(n(n-1)/2, p_intra) number of uniformly drawn inside pairs; a Binomial(#outside pairs, p_inter)
+    number of uniformly drawn pairs with endpoints in different communities (duplicates / self-loops dropped)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     bounds = np.linspace(0, N, n_communities + 1).astype(np.int64)
-    ii, jj = [], []
-    for a in range(n_communities):
-        na = bounds[a + 1] - bounds[a]
-        for b in range(a, n_communities):
-            nb = bounds[b + 1] - bounds[b]
-            pairs = na * (na - 1) // 2 if a == b else na * nb
-            p = p_intra if a == b else p_inter
-            m = int(rng.binomial(pairs, p)) if pairs < 2 ** 62 else int(pairs * p)
-            if m == 0:
-                continue
-            ii.append(rng.integers(bounds[a], bounds[a + 1], size=m, dtype=np.int64))
-            jj.append(rng.integers(bounds[b], bounds[b + 1], size=m, dtype=np.int64))
-    i = np.concatenate(ii) if ii else np.zeros(0, np.int64)
-    j = np.concatenate(jj) if jj else np.zeros(0, np.int64)
+    sizes = np.diff(bounds)
+    comm_of = np.repeat(np.arange(n_communities), sizes)
+    m_in = rng.binomial(sizes * (sizes - 1) // 2, min(1.0, p_intra))
+    cid = np.repeat(np.arange(n_communities), m_in)
+    M_in = int(m_in.sum())
+    i_in = bounds[cid] + (rng.random(M_in) * sizes[cid]).astype(np.int64)
+    j_in = bounds[cid] + (rng.random(M_in) * sizes[cid]).astype(np.int64)
+    out_pairs = (N * (N - 1) // 2) - int((sizes * (sizes - 1) // 2).sum())
+    M_out = int(rng.binomial(out_pairs, min(1.0, p_inter))) if out_pairs > 0 else 0
+    # draw a little more than needed, keep the pairs that cross communities
+    draw = int(M_out * (1.0 + 2.0 / max(n_communities, 2))) + 16
+    io = rng.integers(0, N, size=draw, dtype=np.int64)
+    jo = rng.integers(0, N, size=draw, dtype=np.int64)
+    keep = comm_of[io] != comm_of[jo]
+    io, jo = io[keep][:M_out], jo[keep][:M_out]
+    i = np.concatenate([i_in, io])
+    j = np.concatenate([j_in, jo])
     lo, hi = _unique_undirected(i, j, N)
     return _finish(*_symmetric_csr(lo, hi, N), N, E, rng, dtype)
 

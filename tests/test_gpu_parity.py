@@ -219,3 +219,40 @@ def test_full_size_properties(b200, N, deg):
     xdx = (xr.detach().double() * xr.grad.double()).sum().item()
     hdh = (hr.detach().double() * hr.grad.double()).sum().item()
     assert abs(ydy - xdx) / abs(ydy) < TOL32 and abs(ydy - hdh) / abs(ydy) < TOL32, (ydy, xdx, hdh)
+
+
+def test_forward_is_cuda_graph_capturable(b200):
+    """include/b200gf.h promises no allocation and no host synchronisation inside b200gf_forward: capture one call
+    (hops + tcgen05 contraction) in a CUDA graph, replay it on new input values, compare with an eager call."""
+    from gnn_b200 import graphs, _cabi
+    lib = _cabi.load()
+    N, K, G, F, B = 20000, 4, 64, 64, 1
+    gso = graphs.er_gso(N, 12, seed=7)
+    plan = gso.plan("cuda")
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    h = torch.randn(F, 1, K, G, device="cuda", generator=gen) * 0.1
+    bias = torch.randn(F, device="cuda", generator=gen)
+    xn = torch.randn(N, G, device="cuda", generator=gen)           # node-major operands: the C call does everything
+    y = torch.empty(N, F, device="cuda")
+    wsb = lib.b200gf_workspace_bytes(plan.handle, B, G, F, K, _cabi.NODE_MAJOR, 0)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+
+    def call(stream):
+        rc = lib.b200gf_forward(plan.handle, xn.data_ptr(), _cabi.NODE_MAJOR, G, h.data_ptr(), bias.data_ptr(), 0,
+                                y.data_ptr(), _cabi.NODE_MAJOR, F, ws.data_ptr(), wsb, B, G, F, K, stream)
+        assert rc == 0, lib.b200gf_strerror(rc)
+
+    call(torch.cuda.current_stream().cuda_stream)                  # warm-up (function attributes, tensor-map encoder)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        call(torch.cuda.current_stream().cuda_stream)
+    xn.copy_(torch.randn(N, G, device="cuda", generator=gen))      # new values, same buffers
+    graph.replay()
+    torch.cuda.synchronize()
+    y_graph = y.clone()
+    call(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(y_graph, y)                                 # deterministic kernels: bit-identical
+    ref = b200.LSIGF(h, gso, xn.t().reshape(1, G, N).contiguous(), bias.view(F, 1))
+    assert rel(y.t().reshape(1, F, N).cpu().numpy(), ref.cpu().numpy()) < 1e-5
