@@ -7,8 +7,8 @@ A "step" is one LSIGF forward (alegnn/utils/graphML.py:83-176 semantics) over on
   value  = E * nnz * (K-1) * B * G / t_step     (one op = one multiply-add of one non-zero of S with one feature
            column for one hop), inputs resident in HBM in the reference's [B,G,N] layout, timed with
            CUDA events around exactly K steps after a barrier + synchronize, max over ranks.
-  e2e    = same metric through the public API (gnn_b200.LSIGF) with pinned HOST x and y: H2D and D2H copies inside
-           the timed region.
+  e2e    = same metric through the public API (gnn_b200.LSIGF) with pinned HOST x and y: every step's H2D and D2H copy
+           inside the timed region, overlapped ACROSS steps on two copy streams (class E2EPipeline).
   roofline = the shift kernel (spmm_hop_kernel): algorithmic bytes per launch (gather model) divided by
            its average duration measured live with CUDA events around every hop launch inside the timed region
            (events recorded by the library on the launching stream), against MEASURED_PEAKS.json's HBM copy bandwidth.
@@ -215,10 +215,57 @@ def run_reference_arm(args, w):
 # ------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------
+class E2EPipeline:
+    """End-to-end steps with the copies overlapped across steps: while step i computes, step i+1's input goes host ->
+    device and step i-1's result device -> host on two copy streams (PCIe is full duplex).  Every step still copies ITS
+    input from pinned host memory and ITS result back to pinned host memory; device inputs and host outputs are
+    double-buffered, ordering is by CUDA events, nothing is skipped or cached."""
+
+    def __init__(self, dev, xh, yh_shape, compute):
+        self.xh, self.compute = xh, compute
+        self.s_in, self.s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.xd = [torch.empty(xh.shape, dtype=xh.dtype, device=dev) for _ in range(2)]
+        self.yh = [torch.empty(yh_shape, dtype=xh.dtype).pin_memory() for _ in range(2)]
+        self.ev_in = [torch.cuda.Event() for _ in range(2)]
+        self.ev_cmp = [torch.cuda.Event() for _ in range(2)]
+        self.i = 0
+
+    def step(self):
+        k = self.i & 1
+        self.i += 1
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(self.s_in):
+            self.s_in.wait_event(self.ev_cmp[k])            # the compute of two steps ago has finished reading xd[k]
+            self.xd[k].copy_(self.xh, non_blocking=True)
+            self.ev_in[k].record(self.s_in)
+        cur.wait_event(self.ev_in[k])
+        y = self.compute(self.xd[k])                         # contiguous device result
+        self.ev_cmp[k].record(cur)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(self.ev_cmp[k])
+            self.yh[k].copy_(y, non_blocking=True)
+        y.record_stream(self.s_out)
+
+
+class _JsonOnlyStdout:
+    """The driver reads ONE JSON line from stdout; NCCL / libraries print banners there.  Everything written to fd 1
+    while this is active goes to stderr; `emit` writes the final line to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self._real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self._real, (text + "\n").encode())
+
+
 def run_gpu_arm(args, w):
     import torch.distributed as dist
     import gnn_b200
     from gnn_b200 import _cabi
+    out_fd = _JsonOnlyStdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -274,15 +321,10 @@ def run_gpu_arm(args, w):
         launches_per_step = 1 + 1 + E * (K - 1) + 1             # to_node_major, pack_taps, hops, tap_contract
         # end-to-end through the public API with pinned host buffers
         xh = torch.randn(B, G, N, generator=g).pin_memory()
-        yh = torch.empty(B, F, N).pin_memory()
-
-        def e2e_step():
-            xd = xh.to(dev, non_blocking=True)
-            y = gnn_b200.LSIGF(h, gso, xd, b)
-            yh.copy_(y, non_blocking=True)
-
+        pipe = E2EPipeline(dev, xh, (B, F, N), lambda xd: gnn_b200.to_feature_major(gnn_b200.LSIGF(h, gso, xd, b)))
+        yh = pipe.yh[0]
         with torch.no_grad():
-            ms_e2e = timed(e2e_step, max(3, args.steps // 2), 2)
+            ms_e2e = timed(pipe.step, args.steps, 3)
         # forward + backward (reported beside the headline; SURVEY.md §8d asks for both)
         xg = x.clone().requires_grad_(True)
         hg = h.clone().requires_grad_(True)
@@ -327,14 +369,10 @@ def run_gpu_arm(args, w):
         lib.b200gf_profile_hops(part.plan.handle, 0)
         # e2e: every rank copies its shard in from pinned host memory and its result rows back
         xh = x_local.cpu().pin_memory()
-        yh = torch.empty(part.rows_per_rank, B * F).pin_memory()
-
-        def e2e_step():
-            xd = xh.to(dev, non_blocking=True)
-            yh.copy_(part.forward(h, xd, b, B=B), non_blocking=True)
-
+        pipe = E2EPipeline(dev, xh, (part.rows_per_rank, B * F), lambda xd: part.forward(h, xd, b, B=B).contiguous())
+        yh = pipe.yh[0]
         with torch.no_grad():
-            ms_e2e = timed(e2e_step, max(3, args.steps // 2), 2)
+            ms_e2e = timed(pipe.step, args.steps, 3)
         # my kernels per rank and step: pack_taps, split_w, tc_contract, the hops, and the scatter of the k = 0 slice
         launches_per_step = (E * (K - 1) + 3 + (1 if part.fused else 0)) * world
         if args.mode == "nodes":
@@ -375,7 +413,7 @@ def run_gpu_arm(args, w):
             line["cpu_baseline"] = {"value": ops_s, "unit": "edge-feature-op/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": "reference dense torch.matmul algorithm at N=%d (nnz=%d), 3 forwards of "
                                               "%.2f s; same avgDeg/K/G/F/B" % (n_dense, nnz_d, t)}
-        print(json.dumps(line))
+        out_fd.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

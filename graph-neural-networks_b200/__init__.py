@@ -5,7 +5,7 @@ The directory is called `graph-neural-networks_b200` (not a valid Python identif
 """
 from . import _cabi  # noqa: F401
 from .gso import SparseGSO, Plan, plan_for, clear_plan_cache  # noqa: F401
-from .graphML import LSIGF, GraphFilter, install, uninstall, to_node_major, node_major_ld, padded_ld  # noqa: F401
+from .graphML import LSIGF, GraphFilter, install, uninstall, to_node_major, to_feature_major, node_major_ld, padded_ld  # noqa: F401
 
 from .edgevariant import EVGF, EdgeVariantGF  # noqa: F401,E402
 

@@ -68,6 +68,18 @@ def to_node_major(x):
     return buf, ld
 
 
+def to_feature_major(y):
+    """[B, C, N] result (typically the permuted node-major view LSIGF returns) -> contiguous reference layout, with one
+    coalesced tiled transpose (b200gf_to_feature_major) instead of an element-wise strided copy."""
+    ld = node_major_ld(y)
+    if ld is None or y.device.type != "cuda" or y.dtype not in _ENUM:
+        return y.contiguous()
+    B, C, N = y.shape
+    out = torch.empty((B, C, N), dtype=y.dtype, device=y.device)
+    _cabi.check(_cabi.load().b200gf_to_feature_major(_ENUM[y.dtype], y.data_ptr(), ld, out.data_ptr(), N, B * C, _stream()))
+    return out
+
+
 def _as_bcn_view(buf, B, C, N):
     """node-major [N, ld] buffer -> logical [B, C, N] strided view."""
     return buf[:, :B * C].view(N, B, C).permute(1, 2, 0)
