@@ -279,13 +279,15 @@ def run_gpu_arm(args, w):
         dist.init_process_group("nccl", device_id=dev)
     lib = _cabi.load()
     E, K, G, F, B, N = w["E"], w["K"], w["G"], w["F"], w["B"], w["N"]
-    gso = make_gso(w)
+    tdt = torch.float64 if args.dtype == "f64" else torch.float32      # the reference's examples run in float64
+    es = 8 if args.dtype == "f64" else 4
+    gso = make_gso(w).astype(tdt)
     nnz_e = gso.nnz() // E
     ops_per_step = float(gso.nnz()) * (K - 1) * B * G
     g = torch.Generator().manual_seed(0)
     bound = 1.0 / np.sqrt(G * K)
-    h = ((torch.rand(F, E, K, G, generator=g) * 2 - 1) * bound).to(dev)
-    b = ((torch.rand(F, 1, generator=g) * 2 - 1) * bound).to(dev)
+    h = ((torch.rand(F, E, K, G, generator=g) * 2 - 1) * bound).to(dev, tdt)
+    b = ((torch.rand(F, 1, generator=g) * 2 - 1) * bound).to(dev, tdt)
     peak, peak_src = measured_peak_gbs()
     out = {}
 
@@ -308,7 +310,7 @@ def run_gpu_arm(args, w):
         return float(ms.item()) / steps
 
     if world == 1:
-        x = torch.randn(B, G, N, generator=g).to(dev)           # reference layout, resident in HBM
+        x = torch.randn(B, G, N, generator=g).to(dev, tdt)      # reference layout, resident in HBM
         plan = gso.plan(dev)
         fwd = lambda: gnn_b200.LSIGF(h, gso, x, b)              # noqa: E731  (layout conversion inside the step)
         hops = E * (K - 1)
@@ -320,7 +322,7 @@ def run_gpu_arm(args, w):
         lib.b200gf_profile_hops(plan.handle, 0)
         launches_per_step = 1 + 1 + E * (K - 1) + 1             # to_node_major, pack_taps, hops, tap_contract
         # end-to-end through the public API with pinned host buffers
-        xh = torch.randn(B, G, N, generator=g).pin_memory()
+        xh = torch.randn(B, G, N, generator=g).to(tdt).pin_memory()
         pipe = E2EPipeline(dev, xh, (B, F, N), lambda xd: gnn_b200.to_feature_major(gnn_b200.LSIGF(h, gso, xd, b)))
         yh = pipe.yh[0]
         with torch.no_grad():
@@ -329,7 +331,7 @@ def run_gpu_arm(args, w):
         xg = x.clone().requires_grad_(True)
         hg = h.clone().requires_grad_(True)
         bg = b.clone().requires_grad_(True)
-        dy = torch.randn(B, F, N, generator=g).to(dev)
+        dy = torch.randn(B, F, N, generator=g).to(dev, tdt)
 
         def fwd_bwd():
             xg.grad = hg.grad = bg.grad = None
@@ -340,7 +342,7 @@ def run_gpu_arm(args, w):
                           "value": float(gso.nnz()) * (K - 1) * B * (G + F) / (ms_fb * 1e-3),
                           "note": "forward hops on B*G columns + backward hops on B*F columns per step"}
         C = B * G
-        hop_bytes = hop_algorithmic_bytes(nnz_e, N, C)
+        hop_bytes = hop_algorithmic_bytes(nnz_e, N, C, es)
         hop_avg_ms = float(np.mean(hop_ms)) if len(hop_ms) else float("nan")
         achieved = hop_bytes / (hop_avg_ms * 1e-3) / 1e9
         out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -348,17 +350,17 @@ def run_gpu_arm(args, w):
                            "bytes_per_launch": hop_bytes, "ms_per_launch": hop_avg_ms, "launches_timed": len(hop_ms),
                            "peak_source": peak_src, "kernel_share_of_step": float(np.sum(hop_ms)) / (ms * args.steps)}
         out["e2e"] = {"value": ops_per_step / (ms_e2e * 1e-3), "unit": "edge-feature-op/s",
-                      "h2d_bytes_per_step": xh.numel() * 4, "d2h_bytes_per_step": yh.numel() * 4, "ms_per_step": ms_e2e}
+                      "h2d_bytes_per_step": xh.numel() * es, "d2h_bytes_per_step": yh.numel() * es, "ms_per_step": ms_e2e}
         out["clocks"] = clk.summary()
         parallelism = "single"
     else:
         from gnn_b200.distributed import PartitionedLSIGF
         part = PartitionedLSIGF(gso, mode=args.mode, device=dev, fused=False if args.no_fused else None)
         if args.mode == "nodes":
-            x_local = torch.randn(part.rows_per_rank, B * G, generator=torch.Generator().manual_seed(rank)).to(dev)
+            x_local = torch.randn(part.rows_per_rank, B * G, generator=torch.Generator().manual_seed(rank)).to(dev, tdt)
         else:
             g0, g1 = part.feature_slice(G)
-            x_local = torch.randn(N, B * (g1 - g0), generator=torch.Generator().manual_seed(rank)).to(dev)
+            x_local = torch.randn(N, B * (g1 - g0), generator=torch.Generator().manual_seed(rank)).to(dev, tdt)
         fwd = lambda: part.forward(h, x_local, b, B=B)          # noqa: E731
         hops = E * (K - 1)
         cap = hops * (args.steps + args.warmup)
@@ -380,7 +382,7 @@ def run_gpu_arm(args, w):
         else:
             g0, g1 = part.feature_slice(G)
             c_loc, nnz_loc, rows_loc = B * (g1 - g0), nnz_e, N
-        hop_bytes = hop_algorithmic_bytes(nnz_loc, rows_loc, c_loc)
+        hop_bytes = hop_algorithmic_bytes(nnz_loc, rows_loc, c_loc, es)
         hop_avg_ms = float(np.mean(hop_ms)) if len(hop_ms) else float("nan")
         achieved = hop_bytes / (hop_avg_ms * 1e-3) / 1e9
         out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -389,7 +391,7 @@ def run_gpu_arm(args, w):
                            "bytes_per_launch": hop_bytes, "ms_per_launch": hop_avg_ms, "launches_timed": len(hop_ms),
                            "peak_source": peak_src, "kernel_share_of_step": float(np.sum(hop_ms)) / (ms * args.steps)}
         out["e2e"] = {"value": ops_per_step / (ms_e2e * 1e-3), "unit": "edge-feature-op/s",
-                      "h2d_bytes_per_step": xh.numel() * 4 * world, "d2h_bytes_per_step": yh.numel() * 4 * world,
+                      "h2d_bytes_per_step": xh.numel() * es * world, "d2h_bytes_per_step": yh.numel() * es * world,
                       "ms_per_step": ms_e2e}
         out["clocks"] = clk.summary()
         parallelism = "%s-partition x%d%s" % (args.mode, world, " (fused hop+NVLink scatter)" if part.fused else "")
@@ -398,10 +400,10 @@ def run_gpu_arm(args, w):
         line = {
             "metric": "LSIGF edge-feature ops/s", "value": ops_per_step / (ms * 1e-3), "unit": "edge-feature-op/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": describe(w), "name": args.workload, "nnz": gso.nnz(), "parallelism": parallelism,
+            "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": describe(w).replace("fp32", "fp64" if args.dtype == "f64" else "fp32"), "name": args.workload, "nnz": gso.nnz(), "parallelism": parallelism,
                        "l2": "inputs larger than L2 (x and every z_k are %d MB each; no flush needed)" %
-                             (N * B * G * 4 // 2 ** 20) if N * B * G * 4 > 126 * 2 ** 20 else
+                             (N * B * G * es // 2 ** 20) if N * B * G * es > 126 * 2 ** 20 else
                              "working set fits L2: numbers are L2-warm",
                        "ops_per_step": ops_per_step},
             "gpu_launches": launches_per_step * args.steps,
@@ -443,6 +445,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="features", choices=["nodes", "features"],
                     help="multi-GPU sharding (DESIGN.md §4): feature columns (default) or node rows")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"], help="arithmetic type (headline: f32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fused", action="store_true", help="multi-GPU: NCCL all-to-all instead of the fused NVLink scatter")
     args = ap.parse_args()

@@ -82,7 +82,7 @@ int fetch_csr(HostCsr& A, int64_t n_rows, size_t es, const int64_t* rowptr, cons
   int rc = fetch(A.rowptr, rowptr, (size_t)n_rows + 1);
   if (rc) return rc;
   const int64_t nnz = A.rowptr[n_rows];
-  if (nnz < 0) return B200GF_EINVAL;
+  if (nnz < 0 || (nnz > 0 && (!col || !val))) return B200GF_EINVAL;
   if ((rc = fetch(A.col, col, (size_t)nnz))) return rc;
   if ((rc = fetch(A.val, val, (size_t)nnz * es))) return rc;
   return B200GF_OK;
@@ -163,7 +163,7 @@ int b200gf_plan_create(b200gf_plan** out, int device, int64_t N, int E, const in
   const size_t es = dtype_size(dtype);
   bool all_sym = true;
   for (int e = 0; e < E && rc == B200GF_OK; ++e) {
-    if (!rowptr[e] || !colidx[e] || !vals[e]) { rc = B200GF_EINVAL; break; }
+    if (!rowptr[e]) { rc = B200GF_EINVAL; break; }  // colidx / vals may be null for an edgeless S_e
     HostCsr A, At;
     if ((rc = fetch_csr(A, N, es, rowptr[e], colidx[e], vals[e]))) break;
     if ((rc = validate_csr(A, N, N))) break;
@@ -201,13 +201,13 @@ int b200gf_plan_create_ops(b200gf_plan** out, int device, int64_t n_rows, int64_
   const size_t es = dtype_size(dtype);
   for (int e = 0; e < E && rc == B200GF_OK; ++e) {
     HostCsr A;
-    if (!fwd_rowptr[e] || !fwd_colidx[e] || !fwd_vals[e]) { rc = B200GF_EINVAL; break; }
+    if (!fwd_rowptr[e]) { rc = B200GF_EINVAL; break; }
     if ((rc = fetch_csr(A, n_rows, es, fwd_rowptr[e], fwd_colidx[e], fwd_vals[e]))) break;
     if ((rc = validate_csr(A, n_rows, n_cols))) break;
     if ((rc = upload(A, n_rows, es, p->fwd[e]))) break;
     if (p->has_bwd) {
       HostCsr Bm;
-      if (!bwd_rowptr[e] || !bwd_colidx[e] || !bwd_vals[e]) { rc = B200GF_EINVAL; break; }
+      if (!bwd_rowptr[e]) { rc = B200GF_EINVAL; break; }
       if ((rc = fetch_csr(Bm, n_rows, es, bwd_rowptr[e], bwd_colidx[e], bwd_vals[e]))) break;
       if ((rc = validate_csr(Bm, n_rows, n_cols))) break;
       if ((rc = upload(Bm, n_rows, es, p->bwd[e]))) break;
