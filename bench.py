@@ -355,13 +355,17 @@ def run_gpu_arm(args, w):
         parallelism = "single"
     else:
         from gnn_b200.distributed import PartitionedLSIGF
-        part = PartitionedLSIGF(gso, mode=args.mode, device=dev, fused=False if args.no_fused else None)
+        part = PartitionedLSIGF(gso, mode=args.mode, device=dev, fused=False if args.no_fused else None, fence=args.fence)
         if args.mode == "nodes":
             x_local = torch.randn(part.rows_per_rank, B * G, generator=torch.Generator().manual_seed(rank)).to(dev, tdt)
         else:
             g0, g1 = part.feature_slice(G)
             x_local = torch.randn(N, B * (g1 - g0), generator=torch.Generator().manual_seed(rank)).to(dev, tdt)
         fwd = lambda: part.forward(h, x_local, b, B=B)          # noqa: E731
+        use_graph = args.graph and part.fused and args.fence == "flags" and args.mode == "features"
+        if use_graph:
+            with torch.no_grad():
+                fwd = part.graphed(h, x_local, b, B=B)
         hops = E * (K - 1)
         cap = hops * (args.steps + args.warmup)
         lib.b200gf_profile_hops(part.plan.handle, cap)
@@ -371,7 +375,13 @@ def run_gpu_arm(args, w):
         lib.b200gf_profile_hops(part.plan.handle, 0)
         # e2e: every rank copies its shard in from pinned host memory and its result rows back
         xh = x_local.cpu().pin_memory()
-        pipe = E2EPipeline(dev, xh, (part.rows_per_rank, B * F), lambda xd: part.forward(h, xd, b, B=B).contiguous())
+        if use_graph:
+            def compute(xd):
+                x_local.copy_(xd)
+                return fwd().contiguous()
+        else:
+            compute = lambda xd: part.forward(h, xd, b, B=B).contiguous()   # noqa: E731
+        pipe = E2EPipeline(dev, xh, (part.rows_per_rank, B * F), compute)
         yh = pipe.yh[0]
         with torch.no_grad():
             ms_e2e = timed(pipe.step, args.steps, 3)
@@ -385,7 +395,8 @@ def run_gpu_arm(args, w):
         hop_bytes = hop_algorithmic_bytes(nnz_loc, rows_loc, c_loc, es)
         hop_avg_ms = float(np.mean(hop_ms)) if len(hop_ms) else float("nan")
         achieved = hop_bytes / (hop_avg_ms * 1e-3) / 1e9
-        out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        out["roofline"] = None if not hop_ms else {
+                           "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                            "traffic": None, "kernel": "spmm_hop_kernel (rank 0 shard: %d rows x %d columns, %d nnz)" %
                                                         (rows_loc, c_loc, nnz_loc),
                            "bytes_per_launch": hop_bytes, "ms_per_launch": hop_avg_ms, "launches_timed": len(hop_ms),
@@ -394,7 +405,9 @@ def run_gpu_arm(args, w):
                       "h2d_bytes_per_step": xh.numel() * es * world, "d2h_bytes_per_step": yh.numel() * es * world,
                       "ms_per_step": ms_e2e}
         out["clocks"] = clk.summary()
-        parallelism = "%s-partition x%d%s" % (args.mode, world, " (fused hop+NVLink scatter)" if part.fused else "")
+        parallelism = "%s-partition x%d%s%s" % (args.mode, world,
+                                                " (fused hop+NVLink scatter, %s fence)" % args.fence if part.fused else "",
+                                                ", CUDA graph" if use_graph else "")
 
     if rank == 0:
         line = {
@@ -447,6 +460,9 @@ def main():
                     help="multi-GPU sharding (DESIGN.md §4): feature columns (default) or node rows")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"], help="arithmetic type (headline: f32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fence", default="flags", choices=["flags", "nccl"],
+                    help="multi-GPU fused path: peer flags in symmetric memory (default) or a 4-byte NCCL all-reduce")
+    ap.add_argument("--graph", action="store_true", help="multi-GPU fused path: replay the step as a CUDA graph")
     ap.add_argument("--no-fused", action="store_true", help="multi-GPU: NCCL all-to-all instead of the fused NVLink scatter")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)

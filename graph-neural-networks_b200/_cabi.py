@@ -43,6 +43,8 @@ _SIGNATURES = {
     "b200gf_symm_export": (c_int, [c_vp, c_vp]),
     "b200gf_symm_import": (c_int, [c_vp, PP]),
     "b200gf_symm_close": (c_int, [c_vp]),
+    "b200gf_peer_signal": (c_int, [PP, c_int, c_int, c_vp, c_vp]),
+    "b200gf_peer_wait": (c_int, [c_vp, c_int, c_vp, c_vp]),
     "b200gf_ev_forward": (c_int, [c_int, c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "b200gf_ev_backward": (c_int, [c_int, c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp,
                                    c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

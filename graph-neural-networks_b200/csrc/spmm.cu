@@ -222,3 +222,66 @@ extern "C" int b200gf_symm_close(void* ptr) {
   if (ptr) CUDA_TRY(cudaIpcCloseMemHandle(ptr));
   return B200GF_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Peer fence without NCCL: monotone step counters in symmetric memory.
+//   signal: step = ++(*local_step); make every earlier peer store of this GPU visible (system-scope fence), then write
+//           `step` into slot `my_rank` of every peer's flag array;
+//   wait  : spin until all n_peers slots of MY flag array are >= *local_step.
+// All arguments are fixed addresses, so both kernels can be captured in a CUDA graph and replayed every step.
+// ---------------------------------------------------------------------------------------------------
+namespace b200gf {
+
+struct FlagPeers {
+  unsigned long long* flags[MAX_PEERS];
+};
+
+__global__ void peer_signal_kernel(FlagPeers fp, int n_peers, int my_rank, unsigned long long* local_step) {
+  __shared__ unsigned long long step;
+  if (threadIdx.x == 0) {
+    step = *local_step + 1ull;
+    *local_step = step;
+    __threadfence_system();  // orders this GPU's earlier (previous-kernel) peer stores before the flag stores below
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < n_peers) {
+    unsigned long long* dst = fp.flags[threadIdx.x] + my_rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(step) : "memory");
+  }
+}
+
+__global__ void peer_wait_kernel(const unsigned long long* my_flags, int n_peers, const unsigned long long* local_step) {
+  if ((int)threadIdx.x >= n_peers) return;
+  const unsigned long long want = *local_step;
+  unsigned long long seen = 0;
+  unsigned long long spins = 0;
+  while (true) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(my_flags + threadIdx.x) : "memory");
+    if (seen >= want) break;
+    if (++spins > (1ull << 31)) __trap();  // a peer died: fail loudly instead of hanging the GPU
+    __nanosleep(100);
+  }
+}
+
+}  // namespace b200gf
+
+extern "C" int b200gf_peer_signal(const void* const* peer_flags, int n_peers, int my_rank, void* local_step, void* stream) {
+  if (!peer_flags || n_peers <= 0 || n_peers > b200gf::MAX_PEERS || my_rank < 0 || my_rank >= n_peers || !local_step)
+    return B200GF_EINVAL;
+  b200gf::FlagPeers fp{};
+  for (int i = 0; i < n_peers; ++i) {
+    if (!peer_flags[i]) return B200GF_EINVAL;
+    fp.flags[i] = reinterpret_cast<unsigned long long*>(const_cast<void*>(peer_flags[i]));
+  }
+  b200gf::peer_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(fp, n_peers, my_rank, (unsigned long long*)local_step);
+  LAUNCH_CHECK();
+  return B200GF_OK;
+}
+
+extern "C" int b200gf_peer_wait(const void* my_flags, int n_peers, const void* local_step, void* stream) {
+  if (!my_flags || n_peers <= 0 || n_peers > b200gf::MAX_PEERS || !local_step) return B200GF_EINVAL;
+  b200gf::peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned long long*)my_flags, n_peers,
+                                                             (const unsigned long long*)local_step);
+  LAUNCH_CHECK();
+  return B200GF_OK;
+}

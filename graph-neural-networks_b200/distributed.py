@@ -120,9 +120,12 @@ class SymmetricOperand:
         import ctypes
         self.lib, self.R, self.row_elems = lib, R, row_elems
         es = 4 if dtype == torch.float32 else 8
-        self.buf_bytes = R * row_elems * es
+        self.buf_bytes = (R * row_elems * es + 255) // 256 * 256
+        # layout: [operand 0][operand 1][16 x u64 arrival flags][u64 local step counter]   (alloc zero-fills)
+        self.flags_off = 2 * self.buf_bytes
+        self.step_off = self.flags_off + 128
         mine = ctypes.c_void_p()
-        _cabi.check(lib.b200gf_symm_alloc(ctypes.byref(mine), 2 * self.buf_bytes))
+        _cabi.check(lib.b200gf_symm_alloc(ctypes.byref(mine), 2 * self.buf_bytes + 256))
         self.mine = mine.value
         handle = (ctypes.c_ubyte * 64)()
         _cabi.check(lib.b200gf_symm_export(ctypes.c_void_p(self.mine), handle))
@@ -148,6 +151,15 @@ class SymmetricOperand:
     def local(self, buf):
         return _RawMat(self.mine + buf * self.buf_bytes, self.row_elems)
 
+    def fence(self, rank, stream):
+        """signal + wait on the symmetric flag arrays: returns (on the stream) once every rank's scatters have landed."""
+        import ctypes
+        n = len(self.peers)
+        _cabi.check(self.lib.b200gf_peer_signal(_cabi.ptr_array([p + self.flags_off for p in self.peers]), n, rank,
+                                                ctypes.c_void_p(self.mine + self.step_off), stream))
+        _cabi.check(self.lib.b200gf_peer_wait(ctypes.c_void_p(self.mine + self.flags_off), n,
+                                              ctypes.c_void_p(self.mine + self.step_off), stream))
+
     def close(self):
         import ctypes
         for p in self._opened:
@@ -166,9 +178,10 @@ class PartitionedLSIGF:
     In both, row block p covers global nodes [p*rows_per_rank, (p+1)*rows_per_rank) (the last block is zero-padded).
     """
 
-    def __init__(self, gso, mode="nodes", group=None, device=None, ops=None, fused=None):
-        assert mode in ("nodes", "features")
+    def __init__(self, gso, mode="nodes", group=None, device=None, ops=None, fused=None, fence="flags"):
+        assert mode in ("nodes", "features") and fence in ("flags", "nccl")
         self.mode = mode
+        self.fence = fence          # "flags": peer flags in symmetric memory (no NCCL at all); "nccl": 4-byte all-reduce
         # fused = hop kernels scatter their rows over NVLink themselves (no NCCL collective on the data path);
         # default: on whenever the real CUDA ops run under NCCL with <= 16 ranks
         self._fused_req = fused
@@ -333,7 +346,10 @@ class PartitionedLSIGF:
                 dst = self._buffers(("fz", e, k, Cl), (self.n_pad, ld))
                 self.ops.hop_scatter(self.plan, e, _cabi.HOP_FWD, src, dst, Cl, peers, R, row_elems, t * G + g0, Gl, T * G)
                 src = dst
-        dist.all_reduce(self._flag, group=self.group)       # every rank's scatters precede its contribution
+        if self.fence == "flags":
+            sy.fence(self.rank, self.ops._st())             # every rank's scatters precede its flag store
+        else:
+            dist.all_reduce(self._flag, group=self.group)   # every rank's scatters precede its contribution
         W = self.ops.pack_taps(h, False).reshape(1, T * G, F)
         y = torch.empty((R, _pad_ld(B * F, self.dtype)), dtype=self.dtype, device=self.device)
         bias = None
@@ -342,6 +358,36 @@ class PartitionedLSIGF:
             bias = b.contiguous()
         self.ops.tap_contract([sy.local(buf)], W, bias, y, R, B, T * G, F)
         return y[:, :B * F]
+
+    def graphed(self, h, x_static, b=None, B=1):
+        """CUDA-graph version of the fused features path for a fixed input buffer: two graphs (one per operand buffer)
+        are captured after two eager warm-up calls and replayed alternately, so a step costs one graph launch on the
+        host.  Needs fence="flags" (everything in the step is then a kernel of this library or a device copy).
+        Returns a callable; each call replays one step on the current contents of x_static / h / b."""
+        assert self.mode == "features" and self.fused and self.fence == "flags"
+        for _ in range(2):
+            self.forward(h, x_static, b, B)
+        torch.cuda.synchronize()
+        if self._symm is None:
+            raise RuntimeError("b200gf: graphed() needs the fused path (G/world a multiple of the 16-byte vector width)")
+        assert self._symm.step % 2 == 0
+        graphs, outs = [], []
+        for _ in range(2):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                y = self.forward(h, x_static, b, B)
+            graphs.append(g)
+            outs.append(y)
+        state = {"i": 0}
+
+        def run():
+            k = state["i"] & 1
+            state["i"] += 1
+            graphs[k].replay()
+            return outs[k]
+
+        self._graph_keepalive = (graphs, outs)
+        return run
 
     def _forward_features_rs(self, h, x_cols, b, B):
         """Fallback when G is not divisible by the world size: partial contraction + reduce-scatter of [N, B*F]."""

@@ -160,6 +160,16 @@ int b200gf_symm_export(void* ptr, void* handle64);
 int b200gf_symm_import(const void* handle64, void** ptr);
 int b200gf_symm_close(void* ptr);
 
+/* Peer fence over symmetric memory (no NCCL): every rank owns an array of n_peers uint64 flags and one uint64 step
+ * counter in its symmetric allocation (both zero-initialised).  b200gf_peer_signal increments the local step counter,
+ * issues a system-scope fence (so the peer stores of this rank's earlier kernels are visible first) and writes the new
+ * step into slot my_rank of every peer's flag array (peer_flags: HOST array of n_peers device pointers, own array
+ * included).  b200gf_peer_wait blocks the stream until all n_peers slots of MY flag array have reached the local step.
+ * signal-then-wait after the scatters == "every rank's scatters have landed here".  Fixed addresses only, so both
+ * calls can be captured in a CUDA graph.  A peer that never signals traps the waiting kernel (bounded spin). */
+int b200gf_peer_signal(const void* const* peer_flags, int n_peers, int my_rank, void* local_step, void* stream);
+int b200gf_peer_wait(const void* my_flags, int n_peers, const void* local_step, void* stream);
+
 /* tap contraction: out[n, b*Q + q] = bias + sum_t sum_p Z_t[n, b*P + p] * W[t][p][q]   for n < n_rows.
  * zs: HOST array of T device pointers (node-major, stride z_ld[t]); W: device [T,P,Q] contiguous;
  * bias NULL / [Q] / [Q, n_rows] (bias_per_node).  accumulate != 0 adds to the existing `out`.

@@ -109,6 +109,13 @@ def _worker(rank, world, port, backend, mode, dtype_name, result_q, G=6):
         for _ in range(2):  # twice: buffers are reused across calls
             y_local = part.forward(ht, x_local, bt, B=B)
         assert tuple(y_local.shape) == (R, B * F)
+        if backend == "nccl" and getattr(part, "fused", False) and G % (4 * world) == 0:
+            # the same step replayed as CUDA graphs (peer-flag fence, no NCCL inside): must reproduce the eager result
+            run = part.graphed(ht, x_local, bt, B=B)
+            for _ in range(3):
+                y_graph = run()
+            torch.cuda.synchronize()
+            assert torch.equal(y_graph, y_local), "graph replay differs from the eager fused step"
         ys = [torch.empty_like(y_local) for _ in range(world)]
         dist.all_gather(ys, y_local.contiguous())
         if rank == 0:

@@ -4,7 +4,7 @@
 TAG=${1:-r1m}; NG=${2:-2}
 OUT=gpurun_out/$TAG; mkdir -p $OUT
 echo "== pytest distributed"; timeout 900 python -m pytest tests/test_distributed.py -x -q -m gpu > $OUT/pytest_dist.log 2>&1; echo "exit $?"; tail -5 $OUT/pytest_dist.log
-for CFG in "features" "features --no-fused" "nodes"; do
+for CFG in "features" "features --graph" "features --fence nccl" "nodes"; do
   NAME=$(echo $CFG | tr -d ' -')
   echo "== bench $NG gpus $CFG"
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $NG --steps 10 --warmup 3 --mode $CFG > $OUT/bench_${NG}_$NAME.log 2>&1; echo "exit $?"
