@@ -8,5 +8,6 @@ from .gso import SparseGSO, Plan, plan_for, clear_plan_cache  # noqa: F401
 from .graphML import LSIGF, GraphFilter, install, uninstall, to_node_major, to_feature_major, node_major_ld, padded_ld  # noqa: F401
 
 from .edgevariant import EVGF, EdgeVariantGF  # noqa: F401,E402
+from .pooling import MaxPoolLocal  # noqa: F401,E402
 
-__all__ = ["EVGF", "EdgeVariantGF", "LSIGF", "GraphFilter", "SparseGSO", "Plan", "plan_for", "install", "uninstall"]
+__all__ = ["EVGF", "EdgeVariantGF", "MaxPoolLocal", "LSIGF", "GraphFilter", "SparseGSO", "Plan", "plan_for", "install", "uninstall"]

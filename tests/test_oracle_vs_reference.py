@@ -35,11 +35,12 @@ def test_lsigf_random_cases_vs_reference(seed):
 def test_install_retargets_reference_module():
     import gnn_b200
     gml = ref_import.import_reference()
-    orig = (gml.LSIGF, gml.GraphFilter, gml.EVGF, gml.EdgeVariantGF)
+    orig = (gml.LSIGF, gml.GraphFilter, gml.EVGF, gml.EdgeVariantGF, gml.MaxPoolLocal)
     try:
         gnn_b200.install(gml)
         assert gml.LSIGF is gnn_b200.LSIGF and gml.GraphFilter is gnn_b200.GraphFilter
         assert gml.EVGF is gnn_b200.EVGF and gml.EdgeVariantGF is gnn_b200.EdgeVariantGF
+        assert gml.MaxPoolLocal is gnn_b200.MaxPoolLocal
         # an architecture built now gets the B200 layer, with the reference's parameter names
         import torch.nn as nn
         import alegnn.modules.architectures as archit
@@ -52,4 +53,4 @@ def test_install_retargets_reference_module():
             net(torch.zeros(2, 1, 8, dtype=net.GFL[0].weight.dtype))
     finally:
         gnn_b200.uninstall(gml)
-    assert (gml.LSIGF, gml.GraphFilter, gml.EVGF, gml.EdgeVariantGF) == orig
+    assert (gml.LSIGF, gml.GraphFilter, gml.EVGF, gml.EdgeVariantGF, gml.MaxPoolLocal) == orig
