@@ -3,15 +3,13 @@
 // and src/dst node-major [rows, ld] feature matrices.  This replaces the reference's dense broadcast-batched
 // GEMM torch.matmul(x, S) and is the HBM-bound kernel the roofline in bench.py is quoted on.
 //
-// Mapping (sm_100a, 148 SMs):
-//   * one warp per (row, 128-byte..512-byte column chunk) work item, grid-stride over items in
-//     chunk-major order, so that at any time all resident warps gather from the same column slab
-//     (keeps the gathered slab L2-resident when N * chunk_bytes fits the 126 MB L2);
-//   * L lanes x 16-byte vectors cover the chunk; the 32/L lane groups each take a different neighbour,
-//     so one warp-wide LDG.128 fetches 32/L whole neighbour rows (fully used 32-byte sectors);
-//   * U independent LDG.128 per lane are issued before the FMAs (memory-level parallelism);
-//   * col/val of a row are read once, coalesced (lane i holds entry i) and broadcast with SHFL;
-//   * next row's col/val and the row after's rowptr are prefetched while the current row is gathered.
+// Mapping (sm_100a, 148 SMs) — details and the measured alternatives in spmm_kernels.cuh / profiles/README.md:
+//   * rows of more than 128 bytes: one warp per (row, column chunk), chunk-major grid-stride order (keeps the gathered
+//     column slab L2-resident when it fits), L lanes x 16-byte vectors per neighbour row, 32/L neighbours per LDG.128,
+//     U loads in flight per lane, col/val read once per row and broadcast by SHFL, 48 resident warps per SM,
+//     L2 evict_last policy on the gathered rows;
+//   * narrower rows: several rows per warp (spmm_hop_multirow_kernel);
+//   * optional epilogue: the computed row slice is also stored over NVLink into a peer's buffer (b200gf_hop_scatter).
 #include <cstring>
 
 #include "common.cuh"

@@ -9,8 +9,8 @@
 //     warp-wide LDG.128 fetches 32/L whole neighbour rows (every 32-byte sector fully used);
 //   * U independent LDG.128 per lane are in flight before the FMAs (memory-level parallelism);
 //   * col/val of a row are read once, coalesced (lane i holds entry i), and broadcast with SHFL;
-//   * the next row's col/val and the rowptr pair of the row after that are prefetched while the current row is
-//     being gathered (PF).
+//   * PF (template flag, off in the library): prefetch of the next row's col/val and of the rowptr pair after it while
+//     the current row is gathered — measured slower (registers / issue slots), kept for the sweep tool.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
