@@ -262,17 +262,20 @@ def install(gml=None):
     this also accelerates its hybrid EdgeVariantGF (:2686), jARMA (:592) and GatedGRNN (:1403,:1461) call sites.
     Architectures built AFTER install() get this package's layers (plan cached in addGSO).
     """
-    from . import edgevariant, pooling
+    from . import activations, edgevariant, pooling
     if gml is None:
         import alegnn.utils.graphML as gml
     if id(gml) not in _SAVED:
         _SAVED[id(gml)] = (gml, {n: getattr(gml, n) for n in ("LSIGF", "GraphFilter", "EVGF", "EdgeVariantGF",
-                                                             "MaxPoolLocal")})
+                                                             "MaxPoolLocal", "MaxLocalActivation",
+                                                             "MedianLocalActivation")})
     gml.LSIGF = LSIGF
     gml.GraphFilter = GraphFilter
     gml.EVGF = edgevariant.EVGF
     gml.EdgeVariantGF = edgevariant.EdgeVariantGF
     gml.MaxPoolLocal = pooling.MaxPoolLocal      # same layer, neighbourhoods from the CSR routine (scales past dense N x N)
+    gml.MaxLocalActivation = activations.MaxLocalActivation
+    gml.MedianLocalActivation = activations.MedianLocalActivation
     return gml
 
 
