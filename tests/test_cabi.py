@@ -235,3 +235,28 @@ def test_tensor_core_tap_contract(N, B, P, Q, T, bias_mode):
     print("tc err %.2e  fma err %.2e" % (err, err_fma))
     assert err < 5e-6, err
     assert err_fma < 5e-6, err_fma
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/b200gf.h must be consumable from C (the boundary is a C ABI, not a C++ one): compile a C99 translation
+    unit that includes it and takes the address of every declared function, then link it against the library."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    import gnn_b200
+    names = _header_functions()
+    src = tmp_path / "abi.c"
+    body = "\n".join("    p[%d] = (fn_t)&%s;" % (i, n) for i, n in enumerate(names))
+    src.write_text('#include "b200gf.h"\n#include <stdio.h>\ntypedef void (*fn_t)(void);\nint main(void) {\n'
+                   '    fn_t p[%d];\n%s\n    printf("%%d %%d\\n", b200gf_version(), (int)(p[0] != 0));\n    return 0;\n}\n'
+                   % (len(names), body))
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(gnn_b200._cabi.LIB_PATH)
+    cmd = [gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+           "-L", libdir, "-lb200gf", "-Wl,-rpath," + libdir]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0 and run.stdout.split()[0] == str(gnn_b200._cabi.load().b200gf_version())
