@@ -15,6 +15,9 @@ What is restated here (citations are /root/reference/alegnn/utils/graphML.py):
 * `lsigf_dense_torch` – dense torch CPU port used as the *timed* CPU baseline (same op sequence as the
                         reference: K-1 broadcast batched GEMMs + one contraction GEMM).
 
+A plain-C twin of the forward / backward restatement lives in oracle/lsigf_oracle.c (bound by oracle/c_oracle.py,
+checked by tests/test_c_oracle.py).
+
 Pinning: the reference holds no tests or golden vectors for this path, so the oracle is
 pinned against outputs of the unmodified reference itself, generated in the authoring container by
 `oracle/make_golden.py` and committed under `tests/golden/` (see tests/test_oracle_golden.py), and —
