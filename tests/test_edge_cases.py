@@ -15,7 +15,7 @@ def _rel(a, b):
 
 
 # ------------------------------------------------------------------------------------------------ CPU host logic
-@settings(max_examples=60, deadline=None)
+@settings(max_examples=60, deadline=None, derandomize=True)
 @given(B=st.integers(1, 4), C=st.integers(1, 9), N=st.integers(2, 12), pad=st.integers(0, 5))
 def test_node_major_view_detection(B, C, N, pad):
     import gnn_b200
@@ -32,7 +32,7 @@ def test_node_major_view_detection(B, C, N, pad):
     assert gnn_b200.padded_ld(B * C, torch.float32) % 8 == 0 and gnn_b200.padded_ld(B * C, torch.float64) % 4 == 0
 
 
-@settings(max_examples=30, deadline=None)
+@settings(max_examples=30, deadline=None, derandomize=True)
 @given(N=st.integers(1, 25), E=st.integers(1, 3), seed=st.integers(0, 10 ** 6))
 def test_dense_csr_roundtrip(N, E, seed):
     import scipy.sparse as sp
@@ -51,7 +51,7 @@ def test_dense_csr_roundtrip(N, E, seed):
         assert np.array_equal(v.numpy(), m.data)
 
 
-@settings(max_examples=30, deadline=None)
+@settings(max_examples=30, deadline=None, derandomize=True)
 @given(N=st.integers(1, 30), P=st.integers(1, 5), seed=st.integers(0, 10 ** 6))
 def test_row_partition_covers_everything(N, P, seed):
     """The equal row blocks of the node-sharded path tile [0, P*R) exactly; slices of CSR rows re-assemble the matrix."""
