@@ -283,21 +283,31 @@ def edge_variant_gf_forward(weightEV, weightLSI, bias, S, M, x):
 # --------------------------------------------------------------------------------------------
 # sparse torch CPU restatement: second timed CPU baseline (NOT reference code — the reference has no sparse path)
 # --------------------------------------------------------------------------------------------
-def lsigf_sparse_torch(h, csr_list, x, b=None):
+def prepare_sparse_torch(csr_list, N, dtype):
+    """torch sparse CSR of S_e^T for every e (the forward shift gathers along columns of S_e); done once, untimed."""
+    import torch
+    out = []
+    for (rowptr, col, val) in csr_list:
+        S = torch.sparse_csr_tensor(torch.from_numpy(np.asarray(rowptr, dtype=np.int64)),
+                                    torch.from_numpy(np.asarray(col, dtype=np.int64)),
+                                    torch.from_numpy(np.asarray(val)).to(dtype), size=(N, N))
+        out.append(S.to_sparse_coo().t().to_sparse_csr())
+    return out
+
+
+def lsigf_sparse_torch(h, csr_list, x, b=None, prepared=None):
     """Same arithmetic as lsigf_sparse with torch.sparse CSR x dense products (multi-threaded on the host).
     h [F,E,K,G] torch; csr_list: per e (rowptr, col, val) numpy arrays of S_e; x [B,G,N] torch; returns [B,F,N]."""
     import torch
     F, E, K, G = h.shape
     B, _, N = x.shape
+    if prepared is None:
+        prepared = prepare_sparse_torch(csr_list, N, x.dtype)
     X0 = x.reshape(B * G, N).t().contiguous()                      # node-major [N, C]
     y = torch.zeros(N, B, F, dtype=x.dtype)
     y += torch.einsum("nbg,fg->nbf", X0.view(N, B, G), h[:, :, 0, :].sum(1))
     for e in range(E):
-        rowptr, col, val = csr_list[e]
-        S = torch.sparse_csr_tensor(torch.from_numpy(np.asarray(rowptr, dtype=np.int64)),
-                                    torch.from_numpy(np.asarray(col, dtype=np.int64)),
-                                    torch.from_numpy(np.asarray(val)).to(x.dtype), size=(N, N))
-        St = S.to_sparse_coo().t().to_sparse_csr()                 # forward shift gathers along columns of S_e
+        St = prepared[e]
         cur = X0
         for k in range(1, K):
             cur = torch.sparse.mm(St, cur)
