@@ -256,19 +256,21 @@ _SAVED = {}
 
 
 def install(gml=None):
-    """Point `alegnn.utils.graphML.LSIGF`, `.GraphFilter`, `.EVGF` and `.EdgeVariantGF` at this package.
+    """Point `alegnn.utils.graphML.LSIGF`, `.GraphFilter`, `.EVGF`, `.EdgeVariantGF`, the local pooling / activation
+    layers and the static-GSO recurrent layers at this package.
 
     `GraphFilter.forward` in the reference looks `LSIGF` up as a module global at call time (graphML.py:2137), so
     this also accelerates its hybrid EdgeVariantGF (:2686), jARMA (:592) and GatedGRNN (:1403,:1461) call sites.
     Architectures built AFTER install() get this package's layers (plan cached in addGSO).
     """
-    from . import activations, edgevariant, pooling
+    from . import activations, edgevariant, pooling, recurrent
     if gml is None:
         import alegnn.utils.graphML as gml
     if id(gml) not in _SAVED:
         _SAVED[id(gml)] = (gml, {n: getattr(gml, n) for n in ("LSIGF", "GraphFilter", "EVGF", "EdgeVariantGF",
                                                              "MaxPoolLocal", "MaxLocalActivation",
-                                                             "MedianLocalActivation")})
+                                                             "MedianLocalActivation", "HiddenState",
+                                                             "TimeGatedHiddenState", "NodeGatedHiddenState")})
     gml.LSIGF = LSIGF
     gml.GraphFilter = GraphFilter
     gml.EVGF = edgevariant.EVGF
@@ -276,6 +278,11 @@ def install(gml=None):
     gml.MaxPoolLocal = pooling.MaxPoolLocal      # same layer, neighbourhoods from the CSR routine (scales past dense N x N)
     gml.MaxLocalActivation = activations.MaxLocalActivation
     gml.MedianLocalActivation = activations.MedianLocalActivation
+    # static-GSO recurrent layers: node-major recursion (recurrent.py).  gml.GatedGRNN itself is left alone so that the
+    # reference's EdgeGatedHiddenState (dense per-sample gated GSOs, not on this path) keeps working.
+    gml.HiddenState = recurrent.HiddenState
+    gml.TimeGatedHiddenState = recurrent.TimeGatedHiddenState
+    gml.NodeGatedHiddenState = recurrent.NodeGatedHiddenState
     return gml
 
 

@@ -176,10 +176,49 @@ def gen_evgf(gml):
     print("evgf_cases.npz:", sorted(k for k in out if k.endswith("_y")))
 
 
+def gen_grnn(gml):
+    """GatedGRNN (graphML.py:1292-1527) through the reference's HiddenState / TimeGatedHiddenState /
+    NodeGatedHiddenState layers (graphML.py:3540-4031), fp64: trajectory, input gradient and parameter gradients."""
+    out = {}
+    cases = {"plain": (gml.HiddenState, 14, 3, 5, 2, 4, 3, 2, True),      # (layer, N, B, T, F, H, K, E, bias)
+             "nobias": (gml.HiddenState, 11, 2, 4, 3, 3, 2, 1, False),
+             "time": (gml.TimeGatedHiddenState, 12, 3, 4, 2, 3, 3, 1, True),
+             "node": (gml.NodeGatedHiddenState, 13, 2, 5, 2, 4, 3, 1, True)}
+    for tag, (cls, N, B, T, F, H, K, E, bias) in cases.items():
+        rng = np.random.default_rng(400 + N)
+        S = orc.random_sparse_gso(rng, N, 4, E)
+        torch.manual_seed(N)
+        layer = cls(F, H, K, E=E, bias=bias).double()
+        layer.addGSO(torch.tensor(S))
+        layer.double()                                     # the gate maps are created inside addGSO
+        x = rng.standard_normal((B, T, F, N))
+        z0 = rng.standard_normal((B, H, N))
+        xt = torch.tensor(x, requires_grad=True)
+        z0t = torch.tensor(z0, requires_grad=True)
+        z, zT = layer(xt, z0t)
+        dz = rng.standard_normal(tuple(z.shape))
+        z.backward(torch.tensor(dz))
+        out[tag + "_meta"] = np.array([N, B, T, F, H, K, E, int(bias)])
+        out[tag + "_S"] = S
+        out[tag + "_x"] = x
+        out[tag + "_z0"] = z0
+        out[tag + "_dz"] = dz
+        out[tag + "_z"] = z.detach().numpy()
+        out[tag + "_zT"] = zT.detach().numpy()
+        out[tag + "_dx"] = xt.grad.numpy()
+        out[tag + "_dz0"] = z0t.grad.numpy()
+        for name, p in layer.named_parameters():
+            out[tag + "_p_" + name] = p.detach().numpy()
+            out[tag + "_g_" + name] = p.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, "grnn_cases.npz"), **out)
+    print("grnn_cases.npz:", sorted(k for k in out if k.endswith("_z")))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gml = ref_import.import_reference()
-    gen_lsigf(gml)
-    gen_graphfilter(gml)
-    gen_selectiongnn_cfg1(gml)
-    gen_evgf(gml)
+    only = set(sys.argv[1:])                               # e.g. `python oracle/make_golden.py grnn`
+    for name, gen in (("lsigf", gen_lsigf), ("graphfilter", gen_graphfilter), ("selectiongnn_cfg1", gen_selectiongnn_cfg1),
+                      ("evgf", gen_evgf), ("grnn", gen_grnn)):
+        if not only or name in only:
+            gen(gml)

@@ -54,3 +54,80 @@ def test_install_retargets_reference_module():
     finally:
         gnn_b200.uninstall(gml)
     assert (gml.LSIGF, gml.GraphFilter, gml.EVGF, gml.EdgeVariantGF, gml.MaxPoolLocal) == orig
+
+
+@pytest.mark.parametrize("kind", ["HiddenState", "TimeGatedHiddenState", "NodeGatedHiddenState"])
+@pytest.mark.parametrize("seed", range(3))
+def test_recurrent_layers_vs_reference_live(kind, seed, monkeypatch):
+    """gnn_b200.recurrent against the reference layers (graphML.py:3540-4031) on random shapes.  The dense CPU oracle
+    stands in for the CUDA filter, so this checks the recursion / gating / autograd wiring, not the kernels.  Seeded
+    construction + addGSO consume the RNG in the reference's order, so both layers hold identical parameters."""
+    import gnn_b200
+    from gnn_b200 import recurrent as rec
+    gml = ref_import.import_reference()
+    lsigf = lambda h, S, x, b=None: orc.lsigf_dense_torch(h, S, x, b)  # noqa: E731
+    monkeypatch.setattr(rec, "_lsigf", lsigf)
+    monkeypatch.setattr(gnn_b200.graphML, "LSIGF", lsigf)
+    rng = np.random.default_rng(7000 + seed)
+    N, B, T = int(rng.integers(4, 20)), int(rng.integers(1, 4)), int(rng.integers(1, 6))
+    F, H, K = int(rng.integers(1, 4)), int(rng.integers(1, 5)), int(rng.integers(1, 4))
+    E = int(rng.integers(1, 3)) if kind == "HiddenState" else 1     # the gate GRNNs are built with E = 1 (:3757)
+    bias = bool(seed % 2 == 0)
+    S = torch.tensor(orc.random_sparse_gso(rng, N, 4, E))
+    x, z0 = rng.standard_normal((B, T, F, N)), rng.standard_normal((B, H, N))
+    dz = rng.standard_normal((B, T, H, N))
+    outs = []
+    for mod in (gml, rec):
+        torch.manual_seed(seed)
+        torch.set_default_dtype(torch.float64)
+        try:
+            layer = getattr(mod, kind)(F, H, K, E=E, bias=bias)
+            layer.addGSO(S)
+        finally:
+            torch.set_default_dtype(torch.float32)
+        xt, zt = torch.tensor(x, requires_grad=True), torch.tensor(z0, requires_grad=True)
+        z, zT = layer(xt, zt)
+        z.backward(torch.tensor(dz))
+        outs.append((z.detach().numpy(), zT.detach().numpy(), xt.grad.numpy(), zt.grad.numpy(),
+                     {n: (p.detach().numpy(), p.grad.numpy()) for n, p in layer.named_parameters()}))
+    (z_r, zT_r, dx_r, dz0_r, p_r), (z_m, zT_m, dx_m, dz0_m, p_m) = outs
+    assert sorted(p_r) == sorted(p_m)
+    for n in p_r:
+        assert np.array_equal(p_r[n][0], p_m[n][0]), n             # same init
+        assert _rel(p_m[n][1], p_r[n][1]) < 1e-11, n
+    assert z_m.shape == z_r.shape and zT_m.shape == zT_r.shape
+    assert _rel(z_m, z_r) < 1e-12 and _rel(zT_m, zT_r) < 1e-12
+    assert _rel(dx_m, dx_r) < 1e-11 and _rel(dz0_m, dz0_r) < 1e-11
+
+
+def test_install_retargets_recurrent_layers(monkeypatch):
+    import gnn_b200
+    from gnn_b200 import recurrent as rec
+    import alegnn.modules.architectures as archit
+    gml = ref_import.import_reference()
+    orig = (gml.HiddenState, gml.TimeGatedHiddenState, gml.NodeGatedHiddenState, gml.GatedGRNN, gml.EdgeGatedHiddenState)
+    S = np.eye(6) * 0.5 + np.diag(np.ones(5), 1) * 0.25
+    x = torch.tensor(np.random.default_rng(0).standard_normal((3, 4, 2, 6)), dtype=torch.float32)
+
+    def build_and_run():
+        torch.manual_seed(11)
+        net = archit.GraphRecurrentNN(2, 3, 3, [2, 2], True, torch.tanh, torch.relu, torch.nn.ReLU, [2], S.astype(np.float32))
+        torch.manual_seed(12)                       # z0 is drawn inside splitForward (architectures.py:4547)
+        return net, net(x)
+
+    _, y_ref = build_and_run()
+    try:
+        gnn_b200.install(gml)
+        # the whole architecture through the retargeted layers, with the CPU oracle standing in for the CUDA filter
+        lsigf = lambda h, S_, x_, b=None: orc.lsigf_dense_torch(h, S_, x_, b)  # noqa: E731
+        monkeypatch.setattr(rec, "_lsigf", lsigf)
+        monkeypatch.setattr(gnn_b200.graphML, "LSIGF", lsigf)
+        net, y = build_and_run()
+        assert isinstance(net.hiddenState, gnn_b200.HiddenState) and isinstance(net.outputState, gnn_b200.GraphFilter)
+        assert {"hiddenState.aWeights", "hiddenState.bWeights", "hiddenState.xBias", "hiddenState.zBias",
+                "outputState.weight", "outputState.bias"} <= set(net.state_dict())
+        assert gml.GatedGRNN is orig[3] and gml.EdgeGatedHiddenState is orig[4]   # edge gating stays with the reference
+        assert y.shape == y_ref.shape and torch.allclose(y, y_ref, rtol=1e-5, atol=1e-6)
+    finally:
+        gnn_b200.uninstall(gml)
+    assert (gml.HiddenState, gml.TimeGatedHiddenState, gml.NodeGatedHiddenState) == orig[:3]
