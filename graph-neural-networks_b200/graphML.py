@@ -263,14 +263,15 @@ def install(gml=None):
     this also accelerates its hybrid EdgeVariantGF (:2686), jARMA (:592) and GatedGRNN (:1403,:1461) call sites.
     Architectures built AFTER install() get this package's layers (plan cached in addGSO).
     """
-    from . import activations, edgevariant, pooling, recurrent
+    from . import activations, delayed, edgevariant, pooling, recurrent
     if gml is None:
         import alegnn.utils.graphML as gml
     if id(gml) not in _SAVED:
         _SAVED[id(gml)] = (gml, {n: getattr(gml, n) for n in ("LSIGF", "GraphFilter", "EVGF", "EdgeVariantGF",
                                                              "MaxPoolLocal", "MaxLocalActivation",
                                                              "MedianLocalActivation", "HiddenState",
-                                                             "TimeGatedHiddenState", "NodeGatedHiddenState")})
+                                                             "TimeGatedHiddenState", "NodeGatedHiddenState",
+                                                             "LSIGF_DB", "GraphFilter_DB")})
     gml.LSIGF = LSIGF
     gml.GraphFilter = GraphFilter
     gml.EVGF = edgevariant.EVGF
@@ -283,6 +284,10 @@ def install(gml=None):
     gml.HiddenState = recurrent.HiddenState
     gml.TimeGatedHiddenState = recurrent.TimeGatedHiddenState
     gml.NodeGatedHiddenState = recurrent.NodeGatedHiddenState
+    # batch-/time-varying GSOs: one space-time sparse operator per batch (delayed.py).  GRNN_DB looks LSIGF_DB up as a
+    # module global (graphML.py:1164), so its input-to-hidden filter is retargeted as well.
+    gml.LSIGF_DB = delayed.LSIGF_DB
+    gml.GraphFilter_DB = delayed.GraphFilter_DB
     return gml
 
 

@@ -214,11 +214,58 @@ def gen_grnn(gml):
     print("grnn_cases.npz:", sorted(k for k in out if k.endswith("_z")))
 
 
+def gen_lsigf_db(gml):
+    """LSIGF_DB (graphML.py:977-1094) and GraphFilter_DB (graphML.py:3278-3393): a different GSO per batch element
+    and time step, unit delay per tap; fp64 forward and autograd gradients."""
+    out = {}
+    # (tag, B, T, N, G, F, K, E, bias)
+    cases = [("a", 3, 5, 7, 2, 3, 3, 1, "F1"), ("b", 2, 4, 6, 3, 2, 4, 2, "FN"), ("c", 2, 1, 5, 2, 2, 3, 1, "F1"),
+             ("d", 1, 6, 8, 1, 4, 1, 1, None), ("e", 2, 3, 9, 4, 5, 6, 1, "F1")]      # e: more taps than time steps
+    for (tag, B, T, N, G, F, K, E, bias) in cases:
+        rng = np.random.default_rng(500 + ord(tag))
+        S = np.stack([np.stack([orc.random_sparse_gso(rng, N, 3, E) for _ in range(T)]) for _ in range(B)])  # B,T,E,N,N
+        x = rng.standard_normal((B, T, G, N))
+        bound = 1.0 / np.sqrt(G * K)
+        h = rng.uniform(-bound, bound, (F, E, K, G))
+        b = None if bias is None else rng.uniform(-bound, bound, (F, 1 if bias == "F1" else N))
+        ht, xt = torch.tensor(h, requires_grad=True), torch.tensor(x, requires_grad=True)
+        bt = None if b is None else torch.tensor(b, requires_grad=True)
+        y = gml.LSIGF_DB(ht, torch.tensor(S), xt, bt)
+        dy = rng.standard_normal(tuple(y.shape))
+        y.backward(torch.tensor(dy))
+        key = "f" + tag
+        out[key + "_meta"] = np.array([B, T, N, G, F, K, E, {"F1": 1, "FN": 2, None: 0}[bias]])
+        for name, val in (("S", S), ("x", x), ("h", h), ("dy", dy), ("y", y.detach().numpy()),
+                          ("dh", ht.grad.numpy()), ("dx", xt.grad.numpy())):
+            out[key + "_" + name] = val
+        if b is not None:
+            out[key + "_b"] = b
+            out[key + "_db"] = bt.grad.numpy()
+    # the layer
+    B, T, N, G, F, K, E = 3, 4, 6, 2, 3, 3, 2
+    rng = np.random.default_rng(560)
+    S = np.stack([np.stack([orc.random_sparse_gso(rng, N, 3, E) for _ in range(T)]) for _ in range(B)])
+    torch.manual_seed(560)
+    layer = gml.GraphFilter_DB(G, F, K, E, True).double()
+    layer.addGSO(torch.tensor(S))
+    x = rng.standard_normal((B, T, G, N))
+    xt = torch.tensor(x, requires_grad=True)
+    y = layer(xt)
+    dy = rng.standard_normal(tuple(y.shape))
+    y.backward(torch.tensor(dy))
+    out.update({"layer_meta": np.array([B, T, N, G, F, K, E]), "layer_S": S, "layer_x": x, "layer_dy": dy,
+                "layer_y": y.detach().numpy(), "layer_dx": xt.grad.numpy(),
+                "layer_weight": layer.weight.detach().numpy(), "layer_bias": layer.bias.detach().numpy(),
+                "layer_dweight": layer.weight.grad.numpy(), "layer_dbias": layer.bias.grad.numpy()})
+    np.savez_compressed(os.path.join(OUT, "lsigf_db_cases.npz"), **out)
+    print("lsigf_db_cases.npz:", sorted(k for k in out if k.endswith("_y")))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gml = ref_import.import_reference()
     only = set(sys.argv[1:])                               # e.g. `python oracle/make_golden.py grnn`
     for name, gen in (("lsigf", gen_lsigf), ("graphfilter", gen_graphfilter), ("selectiongnn_cfg1", gen_selectiongnn_cfg1),
-                      ("evgf", gen_evgf), ("grnn", gen_grnn)):
+                      ("evgf", gen_evgf), ("grnn", gen_grnn), ("lsigf_db", gen_lsigf_db)):
         if not only or name in only:
             gen(gml)

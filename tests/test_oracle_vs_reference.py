@@ -103,8 +103,8 @@ def test_recurrent_layers_vs_reference_live(kind, seed, monkeypatch):
 def test_install_retargets_recurrent_layers(monkeypatch):
     import gnn_b200
     from gnn_b200 import recurrent as rec
-    import alegnn.modules.architectures as archit
     gml = ref_import.import_reference()
+    import alegnn.modules.architectures as archit
     orig = (gml.HiddenState, gml.TimeGatedHiddenState, gml.NodeGatedHiddenState, gml.GatedGRNN, gml.EdgeGatedHiddenState)
     S = np.eye(6) * 0.5 + np.diag(np.ones(5), 1) * 0.25
     x = torch.tensor(np.random.default_rng(0).standard_normal((3, 4, 2, 6)), dtype=torch.float32)
@@ -131,3 +131,47 @@ def test_install_retargets_recurrent_layers(monkeypatch):
     finally:
         gnn_b200.uninstall(gml)
     assert (gml.HiddenState, gml.TimeGatedHiddenState, gml.NodeGatedHiddenState) == orig[:3]
+
+
+def test_install_retargets_batch_delay_filter(monkeypatch):
+    """LocalGNN_DB (architecturesTime.py:33-205: two GraphFilter_DB layers + tanh + per-node readout) built from the
+    retargeted module equals the unmodified architecture; the dense CPU oracle applied to the space-time CSR stands in
+    for the CUDA filter."""
+    import gnn_b200
+    from gnn_b200 import delayed
+    gml = ref_import.import_reference()
+    import alegnn.modules.architecturesTime as architTime
+    orig = (gml.LSIGF_DB, gml.GraphFilter_DB)
+    rng = np.random.default_rng(3)
+    B, T, N, E = 3, 5, 7, 2
+    S = torch.tensor(np.stack([np.stack([orc.random_sparse_gso(rng, N, 3, E) for _ in range(T)]) for _ in range(B)]),
+                     dtype=torch.float32)
+    x = torch.tensor(rng.standard_normal((B, T, 2, N)), dtype=torch.float32)
+
+    def build_and_run():
+        torch.manual_seed(21)
+        net = architTime.LocalGNN_DB([2, 4, 3], [3, 2], True, torch.nn.Tanh, [5, 2], E)
+        y = net(x, S)
+        y.sum().backward()
+        return net, y, [p.grad.clone() for p in net.parameters()]
+
+    _, y_ref, g_ref = build_and_run()
+
+    def apply(h, S_, x_big, b_big):
+        csr, M = delayed.block_delay_csr(S_)
+        dense = torch.zeros(len(csr), M, M, dtype=S_.dtype)
+        for e, (rowptr, col, val) in enumerate(csr):
+            dense[e, torch.repeat_interleave(torch.arange(M), rowptr[1:] - rowptr[:-1]), col.long()] = val
+        return orc.lsigf_dense_torch(h, dense, x_big, b_big)
+
+    try:
+        gnn_b200.install(gml)
+        monkeypatch.setattr(delayed, "_apply", apply)
+        net, y, g = build_and_run()
+        assert isinstance(net.GFL[0], gnn_b200.GraphFilter_DB) and isinstance(net.GFL[2], gnn_b200.GraphFilter_DB)
+        assert y.shape == y_ref.shape and torch.allclose(y, y_ref, rtol=1e-5, atol=1e-6)
+        for a, b in zip(g, g_ref):
+            assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
+    finally:
+        gnn_b200.uninstall(gml)
+    assert (gml.LSIGF_DB, gml.GraphFilter_DB) == orig
