@@ -97,6 +97,17 @@ class CudaOps:
             _cabi.i64_array([z.stride(0) for z in zs]), W.data_ptr(), None if bias is None else bias.data_ptr(),
             bias_per_node, out.data_ptr(), out.stride(0), 0, scratch.data_ptr(), sb, self._st()))
 
+    def tap_grad(self, A, vs, n_rows, B, P, Q):
+        """dW[t][p][q] = sum_{n < n_rows, b} A[n, b*P + p] * vs[t][n, b*Q + q]   (b200gf_tap_grad)."""
+        T = len(vs)
+        dW = torch.empty((T, P, Q), dtype=A.dtype, device=A.device)
+        sb = self.lib.b200gf_tap_grad_scratch_bytes(_ENUM[A.dtype], n_rows, B, P, Q, T)
+        scratch = torch.empty(max(int(sb), 1), dtype=torch.uint8, device=A.device)
+        _cabi.check(self.lib.b200gf_tap_grad(
+            _ENUM[A.dtype], n_rows, B, P, Q, T, A.data_ptr(), A.stride(0), _cabi.ptr_array([v.data_ptr() for v in vs]),
+            _cabi.i64_array([v.stride(0) for v in vs]), dW.data_ptr(), scratch.data_ptr(), sb, self._st()))
+        return dW
+
 
 class _RawMat:
     """A [rows, ld] device matrix known only by address (memory mapped from a symmetric allocation)."""
@@ -359,6 +370,133 @@ class PartitionedLSIGF:
         self.ops.tap_contract([sy.local(buf)], W, bias, y, R, B, T * G, F)
         return y[:, :B * F]
 
+    # -- backward ----------------------------------------------------------------------------------
+    def backward(self, h, x_local, dy_rows, B=1, want_db=True):
+        """Gradients of `forward(h, x_local, b, B)` for the upstream gradient dy_rows [rows_per_rank, B*F] of this
+        rank's output rows (zero in the padding rows of the last block).  Collective: every rank calls it.
+        Returns (dh [F, E, K, G], dx_local laid out like x_local, db [F, 1] or None); dh and db are summed over the
+        ranks (identical everywhere), dx_local stays sharded.  SURVEY.md §8 a-8 / §8e: the K-1 shifts of dY use the
+        other operator (rows of S_e), exchanged like the forward's; dh and db end in one small all-reduce."""
+        assert dy_rows.shape[0] == self.rows_per_rank
+        if self.mode == "nodes":
+            return self._backward_nodes(h, x_local, dy_rows, want_db)
+        return self._backward_features(h, x_local, dy_rows, B, want_db)
+
+    def apply(self, h, x_local, b=None, B=1):
+        """Differentiable forward: autograd routes the gradient through `backward` (collective on every rank)."""
+        return _PartitionedFunction.apply(self, B, h, x_local, b)
+
+    def _bias_grad(self, dy_rows, B, F):
+        db = dy_rows[:, :B * F].reshape(self.rows_per_rank, B, F).sum((0, 1))
+        dist.all_reduce(db, group=self.group)
+        return db.reshape(F, 1)
+
+    def _backward_nodes(self, h, x_rows, dy_rows, want_db):
+        F, E, K, G = h.shape
+        R = self.rows_per_rank
+        C = x_rows.shape[1]
+        B = C // G
+        CF = B * F
+        assert E == self.E and C == B * G and x_rows.shape[0] == R and dy_rows.shape[1] == CF
+        ldf = _pad_ld(CF, self.dtype)
+        full0 = self._buffers(("v0", CF), (self.n_pad, ldf))
+        full0[self.r0:self.r1, :CF].copy_(dy_rows)
+        dist.all_gather_into_tensor(full0.view(-1), full0[self.r0:self.r1].reshape(-1), group=self.group)
+        vs = [full0[self.r0:self.r1]]                   # V_{e,k} = S_e^k dY, my rows
+        for e in range(E):
+            src = full0
+            for k in range(1, K):
+                if k == K - 1:
+                    dst_rows = self._buffers(("vl", e, CF), (R, ldf))
+                    self.ops.hop(self.plan, e, _cabi.HOP_BWD, src, dst_rows, CF)
+                else:
+                    full = self._buffers(("v", e, k, CF), (self.n_pad, ldf))
+                    dst_rows = full[self.r0:self.r1]
+                    self.ops.hop(self.plan, e, _cabi.HOP_BWD, src, dst_rows, CF)
+                    dist.all_gather_into_tensor(full.view(-1), dst_rows.reshape(-1), group=self.group)
+                    src = full
+                vs.append(dst_rows)
+        dW = self.ops.tap_grad(x_rows, vs, R, B, G, F)  # [T, G, F]: x_rows^T V_t over my rows
+        dist.all_reduce(dW, group=self.group)
+        dh = _unpack_tap_grads(dW.transpose(1, 2), E, K)
+        dx = torch.empty((R, _pad_ld(C, self.dtype)), dtype=self.dtype, device=self.device)
+        self.ops.tap_contract(vs, self.ops.pack_taps(h, True), None, dx, R, B, F, G)   # sum_t V_t H_t^T, row-local
+        return dh, dx[:, :C], (self._bias_grad(dy_rows, B, F) if want_db else None)
+
+    def _backward_features(self, h, x_cols, dy_rows, B, want_db):
+        """x is column-sharded, y / dY row-sharded.  dh needs Z_t^T dY with Z_t column-sharded: all-gather dY, recompute
+        the shifted slices locally (K-1 hops per e, no communication), contract; the slices of dh are concatenated.
+        dx needs sum_k S^k (dY H_k^T) for my columns: U = dY [H_0^T .. H_{T-1}^T] is row-local (one contraction), one
+        all-to-all turns it from row- to column-sharded, then Horner with the other operator, again without
+        communication.  NVLink bytes per rank: N*B*F*s (all-gather) + T*N*B*(G/P)*s*(P-1)/P (all-to-all)."""
+        F, E, K, G = h.shape
+        P = self.world
+        R = self.rows_per_rank
+        T = 1 + E * (K - 1)
+        per = (G + P - 1) // P
+        g0, g1 = self.feature_slice(G)
+        Gl = g1 - g0
+        Cl = B * Gl
+        CF = B * F
+        assert dy_rows.shape[1] == CF
+        ldf = _pad_ld(CF, self.dtype)
+        ld = _pad_ld(max(Cl, 1), self.dtype)
+        dyf = self._buffers(("bdy", CF), (self.n_pad, ldf))
+        dyf[self.r0:self.r1, :CF].copy_(dy_rows)
+        dist.all_gather_into_tensor(dyf.view(-1), dyf[self.r0:self.r1].reshape(-1), group=self.group)
+        # ---- dh: my in-feature columns
+        dWl = torch.zeros((T, F, per), dtype=self.dtype, device=self.device)
+        if Gl > 0:
+            assert x_cols.shape[0] == self.N and x_cols.shape[1] == Cl
+            z0 = self._buffers(("fz0", Cl), (self.n_pad, ld))
+            z0[:self.N, :Cl].copy_(x_cols)
+            zs = [z0]
+            for e in range(E):
+                src = z0
+                for k in range(1, K):
+                    dst = self._buffers(("fz", e, k, Cl), (self.n_pad, ld))
+                    self.ops.hop(self.plan, e, _cabi.HOP_FWD, src, dst, Cl)
+                    zs.append(dst)
+                    src = dst
+            dWl[:, :, :Gl] = self.ops.tap_grad(dyf, zs, self.N, B, F, Gl)       # [T, F, Gl] = dY^T Z_t
+        parts = [torch.empty_like(dWl) for _ in range(P)]
+        dist.all_gather(parts, dWl, group=self.group)
+        dW = torch.cat([parts[p][:, :, :max(0, min(G, (p + 1) * per) - min(G, p * per))] for p in range(P)], dim=2)
+        dh = _unpack_tap_grads(dW, E, K)
+        # ---- dx: U[n, b, t, g] = sum_f dY[n, b, f] h_t[f, g] for my rows, every g
+        Wt = self.ops.pack_taps(h, True)                                         # [T, F, G]
+        Wall = Wt.permute(1, 0, 2).reshape(1, F, T * G).contiguous()
+        U = torch.empty((R, _pad_ld(B * T * G, self.dtype)), dtype=self.dtype, device=self.device)
+        self.ops.tap_contract([dyf[self.r0:self.r1]], Wall, None, U, R, B, F, T * G)
+        Uv = U[:, :B * T * G].reshape(R, B, T, G)
+        if P * per != G:
+            Uv = torch.cat((Uv, torch.zeros((R, B, T, P * per - G), dtype=self.dtype, device=self.device)), dim=3)
+        send = Uv.reshape(R, B, T, P, per).permute(3, 0, 1, 2, 4).contiguous()   # [P, R, B, T, per]: block p -> rank p
+        recv = torch.empty_like(send)                                             # block q: rows of rank q, my columns
+        all_to_all_blocks(recv, send, self.group)
+        dx = None
+        if Gl > 0:
+            Ub = self._buffers(("bU", T, Cl), (T, self.n_pad, ld))
+            Ub[:, :, :Cl] = recv[..., :Gl].permute(3, 0, 1, 2, 4).reshape(T, self.n_pad, Cl)
+            dxb = Ub[0]                                  # k = 0 term (shared by every e)
+            tmp = [self._buffers(("bw", i, Cl), (self.n_pad, ld)) for i in range(2)]
+            for e in range(E):
+                if K == 1:
+                    break
+                w = Ub[1 + e * (K - 1) + (K - 2)]        # W_{e,K-1} = U_{e,K-1}
+                for k in range(K - 2, -1, -1):           # W_{e,k} = U_{e,k} + S_e W_{e,k+1}
+                    out = tmp[k & 1]
+                    self.ops.hop(self.plan, e, _cabi.HOP_BWD, w, out, Cl)
+                    if k > 0:
+                        out[:self.N, :Cl] += Ub[1 + e * (K - 1) + (k - 1)][:self.N, :Cl]
+                        w = out
+                    else:
+                        dxb[:self.N, :Cl] += out[:self.N, :Cl]
+            dx = dxb[:self.N, :Cl]
+        else:
+            dx = torch.zeros((self.N, 0), dtype=self.dtype, device=self.device)
+        return dh, dx, (self._bias_grad(dy_rows, B, F) if want_db else None)
+
     def graphed(self, h, x_static, b=None, B=1):
         """CUDA-graph version of the fused features path for a fixed input buffer: two graphs (one per operand buffer)
         are captured after two eager warm-up calls and replayed alternately, so a step costs one graph launch on the
@@ -437,6 +575,44 @@ def all_to_all_rows(out, inp, group=None):
     for p in range(P):
         out[p].copy_(bufs[p].view(P, out.shape[1], out.shape[2])[r])
     return None
+
+
+def all_to_all_blocks(out, inp, group=None):
+    """out[q] <- rank q's inp[rank]   (inp, out: [P, ...] contiguous, equal blocks).  gloo: all-gather + slice."""
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all_single(out.view(-1), inp.view(-1), group=group)
+        return
+    P = dist.get_world_size(group)
+    r = dist.get_rank(group)
+    bufs = [torch.empty_like(inp) for _ in range(P)]
+    dist.all_gather(bufs, inp, group=group)
+    for q in range(P):
+        out[q].copy_(bufs[q][r])
+
+
+def _unpack_tap_grads(dW, E, K):
+    """dW [T, F, G] in the packed term order (t = 0: the k = 0 tap shared by every e; t = 1 + e*(K-1) + (k-1)) ->
+    dh [F, E, K, G] (the k = 0 gradient is the same for every e: all of them multiply the unshifted x)."""
+    T, F, G = dW.shape
+    dh = torch.empty((F, E, K, G), dtype=dW.dtype, device=dW.device)
+    dh[:, :, 0, :] = dW[0].unsqueeze(1)
+    if K > 1:
+        dh[:, :, 1:, :] = dW[1:].reshape(E, K - 1, F, G).permute(2, 0, 1, 3)
+    return dh
+
+
+class _PartitionedFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, part, B, h, x_local, b):
+        ctx.part, ctx.B, ctx.has_bias = part, B, b is not None
+        ctx.save_for_backward(h, x_local)
+        return part.forward(h.detach(), x_local.detach(), None if b is None else b.detach(), B)
+
+    @staticmethod
+    def backward(ctx, dy):
+        h, x_local = ctx.saved_tensors
+        dh, dx, db = ctx.part.backward(h, x_local, dy.contiguous(), ctx.B, want_db=ctx.has_bias)
+        return None, None, dh, dx, db
 
 
 def reduce_scatter_rows(out_rows, full, group=None):

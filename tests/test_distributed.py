@@ -31,15 +31,16 @@ class OracleOps:
 
     def make_plan_ops(self, fwd, bwd, n_rows, n_cols, dtype):
         import scipy.sparse as sp
-        return {"fwd": [sp.csr_matrix((v, c, r), shape=(n_rows, n_cols)) for (r, c, v) in fwd]}
+        mk = lambda ops: [sp.csr_matrix((v, c, r), shape=(n_rows, n_cols)) for (r, c, v) in ops]  # noqa: E731
+        return {"fwd": mk(fwd), "bwd": None if bwd is None else mk(bwd)}
 
     def make_plan_full(self, gso):
         import scipy.sparse as sp
-        return {"fwd": [sp.csr_matrix((v, c, r), shape=(gso.N, gso.N)).T.tocsr() for (r, c, v) in gso.csr]}
+        full = [sp.csr_matrix((v, c, r), shape=(gso.N, gso.N)) for (r, c, v) in gso.csr]
+        return {"fwd": [m.T.tocsr() for m in full], "bwd": full}     # fwd gathers with rows of S^T, bwd with rows of S
 
     def hop(self, plan, e, direction, src, dst, C):
-        assert direction == 0
-        A = plan["fwd"][e]                      # like b200gf_hop: reads n_cols rows of src, writes n_rows rows of dst
+        A = plan["fwd" if direction == 0 else "bwd"][e]   # like b200gf_hop: reads n_cols rows of src, writes n_rows rows of dst
         out = A @ src[:A.shape[1], :C].numpy()
         dst[:A.shape[0], :C] = torch.from_numpy(np.ascontiguousarray(out))
 
@@ -49,7 +50,12 @@ class OracleOps:
         for e in range(E):
             for k in range(1, K):
                 W.append(h[:, e, k, :].t())
-        return torch.stack(W).contiguous()
+        W = torch.stack(W)                                     # [T, G, F]
+        return (W.transpose(1, 2) if transpose else W).contiguous()
+
+    def tap_grad(self, A, vs, n_rows, B, P, Q):
+        a = A[:n_rows, :B * P].reshape(n_rows, B, P)
+        return torch.stack([torch.einsum("nbp,nbq->pq", a, v[:n_rows, :B * Q].reshape(n_rows, B, Q)) for v in vs])
 
     def tap_contract(self, zs, W, bias, out, n_rows, B, P, Q, bias_per_node=0):
         acc = torch.zeros(n_rows, B, Q, dtype=out.dtype)
@@ -116,6 +122,24 @@ def _worker(rank, world, port, backend, mode, dtype_name, result_q, G=6):
                 y_graph = run()
             torch.cuda.synchronize()
             assert torch.equal(y_graph, y_local), "graph replay differs from the eager fused step"
+        # backward through the autograd wrapper (collective on every rank): dh, db summed over ranks, dx sharded like x
+        dy = np.random.default_rng(99).standard_normal((B, F, N))
+        dyp = torch.zeros(part.n_pad, B * F, dtype=dtype)
+        dyp[:N] = torch.tensor(dy, dtype=dtype).reshape(B * F, N).t()
+        hg, xg, bg = (t.clone().requires_grad_(True) for t in (ht, x_local, bt))
+        part.apply(hg, xg, bg, B).backward(dyp[part.r0:part.r1].to(dev))
+        if mode == "nodes":
+            dxs = [torch.empty_like(xg.grad) for _ in range(world)]
+            dist.all_gather(dxs, xg.grad.contiguous())
+            dx_nm = torch.cat(dxs)[:N].reshape(N, B, G)
+        else:
+            per = (G + world - 1) // world
+            mine = torch.zeros(N, B, per, dtype=dtype, device=dev)
+            mine[:, :, :g1 - g0] = xg.grad.reshape(N, B, g1 - g0)
+            dxs = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(dxs, mine)
+            dx_nm = torch.cat(dxs, dim=2)[:, :, :G] if G % world == 0 else \
+                torch.cat([d[:, :, :max(0, min(G, (p + 1) * per) - min(G, p * per))] for p, d in enumerate(dxs)], dim=2)
         ys = [torch.empty_like(y_local) for _ in range(world)]
         dist.all_gather(ys, y_local.contiguous())
         if rank == 0:
@@ -125,7 +149,12 @@ def _worker(rank, world, port, backend, mode, dtype_name, result_q, G=6):
             mr = [sp.csr_matrix((m.data.astype(npd).astype(np.float64), m.indices, m.indptr), shape=m.shape) for m in mats]
             r64 = lambda a: a.astype(npd).astype(np.float64)  # noqa: E731
             y_ref = orc.lsigf_sparse(r64(h), mr, r64(x), r64(b))
-            result_q.put(float(np.abs(y - y_ref).max() / np.abs(y_ref).max()))
+            rel = lambda a, r: float(np.abs(a - r).max() / np.abs(r).max())  # noqa: E731
+            dh_ref, dx_ref, db_ref = orc.lsigf_grads_sparse(r64(h), mr, r64(x), r64(dy), (F, 1))
+            errs = [rel(y, y_ref), rel(hg.grad.cpu().double().numpy(), dh_ref),
+                    rel(dx_nm.cpu().double().numpy().transpose(1, 2, 0), dx_ref),
+                    rel(bg.grad.cpu().double().numpy(), db_ref)]
+            result_q.put(max(errs))
     finally:
         dist.destroy_process_group()
 
