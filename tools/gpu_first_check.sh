@@ -1,0 +1,17 @@
+#!/bin/bash
+# First GPU call of a round: run the GPU legs that were written without GPU access (static-GSO recurrent layers,
+# batch-/time-varying filter, and — with >= 2 GPUs — the multi-GPU backward), each file on its own so that one failure
+# does not hide the others, then the full GPU suite and the smoke test.
+#   Usage (repo root, under gpurun):  bash tools/gpu_first_check.sh [tag]
+TAG=${1:-first}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > $OUT/gpu.txt 2>&1
+for T in test_widen_recurrent test_widen_delayed; do
+  echo "== $T"; timeout 600 python -m pytest tests/$T.py -q -m gpu > $OUT/$T.log 2>&1; echo "exit $?"; tail -15 $OUT/$T.log
+done
+if [ "$(nvidia-smi -L | wc -l)" -ge 2 ]; then
+  echo "== test_widen_distributed (NCCL, forward + backward)"; timeout 900 python -m pytest tests/test_widen_distributed.py -q -m gpu > $OUT/test_distributed.log 2>&1; echo "exit $?"; tail -15 $OUT/test_distributed.log
+fi
+echo "== full GPU suite"; timeout 1200 python -m pytest tests -x -q -m gpu > $OUT/pytest_gpu.log 2>&1; echo "exit $?"; tail -4 $OUT/pytest_gpu.log
+echo "== smoke"; timeout 300 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; echo "exit $?"; tail -2 $OUT/smoke.log
