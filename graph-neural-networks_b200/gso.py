@@ -61,6 +61,20 @@ class SparseGSO:
         csr = [dense_to_csr(S[e]) for e in range(S.shape[0])]
         return cls([(r.cpu().numpy(), c.cpu().numpy(), v.cpu().numpy()) for (r, c, v) in csr], S.shape[1])
 
+    @classmethod
+    def from_torch_sparse(cls, S, dtype=None):
+        """torch sparse GSO: one [E, N, N] tensor (COO, or batched CSR) or a list of E [N, N] sparse tensors (COO / CSR /
+        CSC, any device).  Duplicate COO entries are summed; columns come out sorted inside every row."""
+        import scipy.sparse as sp
+        mats2d = list(S) if isinstance(S, (list, tuple)) else [S[e] for e in range(S.shape[0])]
+        mats = []
+        for m in mats2d:
+            assert m.dim() == 2 and m.shape[0] == m.shape[1]
+            c = (m if m.layout == torch.sparse_coo else m.to_sparse_coo()).coalesce().cpu()
+            idx = c.indices().numpy()
+            mats.append(sp.csr_matrix((c.values().numpy(), (idx[0], idx[1])), shape=tuple(m.shape)))
+        return cls.from_scipy(mats, dtype)
+
     # -- tensor-like surface -------------------------------------------------------------------------
     def to(self, *args, **kwargs):
         return self  # plans are created per device on demand
@@ -220,7 +234,18 @@ def plan_for(S, device=None):
         raise NotImplementedError("b200gf: gradients w.r.t. the GSO are not part of the LSIGF path "
                                   "(the reference keeps S as a plain attribute, graphML.py:2099)")
     if S.layout != torch.strided:
-        S = S.to_dense()
+        # torch sparse GSO (SURVEY §8b extension): never densified — converted once to host CSR, cached per tensor
+        assert S.dim() == 3 and S.shape[1] == S.shape[2]
+        key = ("sparse", id(S), S._version)
+        hit = _PLAN_CACHE.get(key)
+        if hit is None or hit[0]() is not S:
+            if len(_PLAN_CACHE) >= _PLAN_CACHE_MAX:
+                _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
+            hit = (weakref.ref(S), SparseGSO.from_torch_sparse(S))
+            _PLAN_CACHE[key] = hit
+        if device is None:
+            device = S.device if S.device.type == "cuda" else torch.device("cuda", torch.cuda.current_device())
+        return hit[1].plan(device)
     assert S.dim() == 3 and S.shape[1] == S.shape[2]
     if S.device.type != "cuda":
         raise RuntimeError("b200gf: LSIGF needs CUDA tensors (there is no CPU fallback); got GSO on %s" % S.device)

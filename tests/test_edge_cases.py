@@ -51,6 +51,32 @@ def test_dense_csr_roundtrip(N, E, seed):
         assert np.array_equal(v.numpy(), m.data)
 
 
+@pytest.mark.filterwarnings("ignore:Sparse")
+def test_torch_sparse_gso_inputs():
+    """The GSO may arrive as a torch sparse tensor (SURVEY.md §8b extension): [E, N, N] COO or batched CSR, or a list of
+    2-D COO / CSR / CSC tensors — same host CSR as the dense route, duplicates summed, never densified."""
+    import gnn_b200
+    rng = np.random.default_rng(0)
+    E, N = 2, 9
+    pattern = rng.random((N, N)) < 0.3
+    D = torch.tensor(rng.standard_normal((E, N, N)) * pattern)           # same pattern for every e: batched CSR exists
+    ref = gnn_b200.SparseGSO.from_dense(D)
+
+    def same(g):
+        return g.shape == ref.shape and g.dtype == ref.dtype and \
+            all(np.array_equal(a, b) for x, y in zip(g.csr, ref.csr) for a, b in zip(x, y))
+
+    assert same(gnn_b200.SparseGSO.from_torch_sparse(D.to_sparse()))
+    assert same(gnn_b200.SparseGSO.from_torch_sparse(D.to_sparse_csr()))
+    assert same(gnn_b200.SparseGSO.from_torch_sparse([D[e].to_sparse_csr() for e in range(E)]))
+    assert same(gnn_b200.SparseGSO.from_torch_sparse([D[e].to_sparse_csc() for e in range(E)]))
+    dup = torch.sparse_coo_tensor(torch.tensor([[0, 0, 2], [1, 1, 0]]), torch.tensor([1.0, 2.0, 5.0]), (3, 3))
+    assert torch.equal(gnn_b200.SparseGSO.from_torch_sparse([dup]).to_dense()[0],
+                       torch.tensor([[0.0, 3.0, 0.0], [0.0, 0.0, 0.0], [5.0, 0.0, 0.0]]))
+    f32 = gnn_b200.SparseGSO.from_torch_sparse(D.to_sparse(), dtype=torch.float32)
+    assert f32.dtype == torch.float32 and np.array_equal(f32.csr[0][2], ref.csr[0][2].astype(np.float32))
+
+
 @settings(max_examples=30, deadline=None, derandomize=True)
 @given(N=st.integers(1, 30), P=st.integers(1, 5), seed=st.integers(0, 10 ** 6))
 def test_row_partition_covers_everything(N, P, seed):

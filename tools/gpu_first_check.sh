@@ -7,7 +7,7 @@ TAG=${1:-first}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > $OUT/gpu.txt 2>&1
-for T in test_widen_recurrent test_widen_delayed; do
+for T in test_widen_recurrent test_widen_delayed test_widen_sparse_inputs; do
   echo "== $T"; timeout 600 python -m pytest tests/$T.py -q -m gpu > $OUT/$T.log 2>&1; echo "exit $?"; tail -15 $OUT/$T.log
 done
 if [ "$(nvidia-smi -L | wc -l)" -ge 2 ]; then
