@@ -15,3 +15,6 @@ if [ "$(nvidia-smi -L | wc -l)" -ge 2 ]; then
 fi
 echo "== full GPU suite"; timeout 1200 python -m pytest tests -x -q -m gpu > $OUT/pytest_gpu.log 2>&1; echo "exit $?"; tail -4 $OUT/pytest_gpu.log
 echo "== smoke"; timeout 300 python __graft_entry__.py smoke > $OUT/smoke.log 2>&1; echo "exit $?"; tail -2 $OUT/smoke.log
+# next-kernel probe (standalone, not part of the library): tensor-core tap gradient, correctness + timing at R = 1M
+echo "== tapgrad_tc_probe"; nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o /tmp/tapgrad_tc_probe tools/tapgrad_tc_probe.cu > $OUT/probe_build.log 2>&1 \
+  && timeout 120 /tmp/tapgrad_tc_probe time > $OUT/tapgrad_tc_probe.log 2>&1; echo "exit $?"; tail -8 $OUT/tapgrad_tc_probe.log
