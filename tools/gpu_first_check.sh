@@ -7,6 +7,7 @@ TAG=${1:-first}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > $OUT/gpu.txt 2>&1
+export B200GF_STRICT_WIDEN=1   # report the first hardware run of these legs as ordinary pass / fail
 for T in test_widen_recurrent test_widen_delayed test_widen_sparse_inputs; do
   echo "== $T"; timeout 600 python -m pytest tests/$T.py -q -m gpu > $OUT/$T.log 2>&1; echo "exit $?"; tail -15 $OUT/$T.log
 done
