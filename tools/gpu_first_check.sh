@@ -19,3 +19,5 @@ echo "== smoke"; timeout 300 python __graft_entry__.py smoke > $OUT/smoke.log 2>
 # next-kernel probe (standalone, not part of the library): tensor-core tap gradient, correctness + timing at R = 1M
 echo "== tapgrad_tc_probe"; nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o /tmp/tapgrad_tc_probe tools/tapgrad_tc_probe.cu > $OUT/probe_build.log 2>&1 \
   && timeout 120 /tmp/tapgrad_tc_probe time > $OUT/tapgrad_tc_probe.log 2>&1; echo "exit $?"; tail -8 $OUT/tapgrad_tc_probe.log
+echo "== contract_f64_probe"; nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o /tmp/contract_f64_probe tools/contract_f64_probe.cu >> $OUT/probe_build.log 2>&1 \
+  && timeout 120 /tmp/contract_f64_probe time > $OUT/contract_f64_probe.log 2>&1; echo "exit $?"; tail -8 $OUT/contract_f64_probe.log
