@@ -201,3 +201,17 @@ def test_partitioned_nccl_world2(mode, G, dtype_name, tol):
         pytest.skip("needs 2 GPUs")
     err = _run("nccl", mode, dtype_name, G=G, backward=False)    # backward over NCCL: tests/test_widen_distributed.py
     assert err < tol, err
+
+
+def test_unpack_tap_grads_is_the_adjoint_of_pack_taps():
+    """dh = unpack(dW) must satisfy <dh, h'> = sum_t <dW_t, pack(h')_t> for every h' (the k = 0 tap is shared by all e)."""
+    from gnn_b200.distributed import _unpack_tap_grads
+    rng = np.random.default_rng(4)
+    for (F, E, K, G) in [(3, 1, 1, 2), (2, 2, 3, 4), (4, 3, 2, 1), (1, 1, 5, 3)]:
+        T = 1 + E * (K - 1)
+        dW = torch.tensor(rng.standard_normal((T, F, G)))
+        hp = torch.tensor(rng.standard_normal((F, E, K, G)))
+        packed = OracleOps().pack_taps(hp, True)                     # [T, F, G]
+        dh = _unpack_tap_grads(dW, E, K)
+        assert dh.shape == hp.shape
+        assert abs(float((dh * hp).sum() - (dW * packed).sum())) < 1e-10

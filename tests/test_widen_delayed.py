@@ -169,3 +169,40 @@ def test_gpu_flocking_sized_batch_against_batched_matmul():
     assert float((y - ref).abs().max() / ref.abs().max()) < 1e-12
     y32 = delayed.LSIGF_DB(h.float(), S.float(), x.float(), b.float())
     assert float((y32.double() - ref).abs().max() / ref.abs().max()) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ CPU, random shapes
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=25, deadline=None, derandomize=True)
+@given(B=st.integers(1, 3), T=st.integers(1, 5), N=st.integers(1, 6), G=st.integers(1, 3), F=st.integers(1, 3),
+       K=st.integers(1, 5), E=st.integers(1, 2), bias=st.sampled_from([None, "F1", "FN"]), seed=st.integers(0, 10 ** 6))
+def test_space_time_filter_equals_delayed_products(B, T, N, G, F, K, E, bias, seed):
+    """LSIGF_DB through the space-time operator == the definition (graphML.py:990-997): per-(b, t) dense products with
+    one unit delay per tap and zero history, for random shapes incl. T = 1, N = 1, K > T."""
+    from gnn_b200 import delayed
+    rng = np.random.default_rng(seed)
+    S = torch.tensor(rng.standard_normal((B, T, E, N, N)) * (rng.random((B, T, E, N, N)) < 0.6))
+    x = torch.tensor(rng.standard_normal((B, T, G, N)))
+    h = torch.tensor(rng.standard_normal((F, E, K, G)))
+    b = None if bias is None else torch.tensor(rng.standard_normal((F, 1 if bias == "F1" else N)))
+
+    def apply(h_, S_, x_big, b_big):
+        csr, M = delayed.block_delay_csr(S_)
+        return orc.lsigf_dense_torch(h_, _dense_from_csr(csr, M, S_.dtype), x_big, b_big)
+
+    old = delayed._apply
+    delayed._apply = apply
+    try:
+        y = delayed.LSIGF_DB(h, S, x, b)
+    finally:
+        delayed._apply = old
+    z, ref = x.unsqueeze(2).expand(B, T, E, G, N), 0.0
+    for k in range(K):
+        if k > 0:
+            z = torch.matmul(torch.cat((torch.zeros_like(z[:, :1]), z[:, :-1]), 1), S)
+        ref = ref + torch.einsum("feg,btegn->btfn", h[:, :, k], z)
+    if b is not None:
+        ref = ref + b
+    assert y.shape == (B, T, F, N) and torch.allclose(y, ref, rtol=1e-12, atol=1e-12)
