@@ -412,6 +412,18 @@ def run_gpu_arm(args, w):
         yh = pipe.yh[0]
         with torch.no_grad():
             ms_e2e = timed(pipe.step, args.steps, 3)
+        if args.bwd:   # opt-in: forward + the collective backward (dh, db all-reduced; dx sharded like x)
+            dy_rows = torch.randn(part.rows_per_rank, B * F, generator=torch.Generator().manual_seed(100 + rank)).to(dev, tdt)
+
+            def fwd_bwd():
+                part.forward(h, x_local, b, B=B)
+                part.backward(h, x_local, dy_rows, B=B, want_db=True)
+
+            with torch.no_grad():
+                ms_fb = timed(fwd_bwd, max(3, args.steps // 2), 2)
+            out["fwd_bwd"] = {"ms_per_step": ms_fb, "unit": "edge-feature-op/s",
+                              "value": float(gso.nnz()) * (K - 1) * B * (G + F) / (ms_fb * 1e-3),
+                              "note": "partitioned forward + backward (NCCL exchanges in the backward)"}
         # my kernels per rank and step: pack_taps, split_w, tc_contract, the hops, and the scatter of the k = 0 slice
         launches_per_step = (E * (K - 1) + 3 + (1 if part.fused else 0)) * world
         if args.mode == "nodes":
@@ -496,6 +508,7 @@ def main():
                     help="multi-GPU fused path: peer flags in symmetric memory (default) or a 4-byte NCCL all-reduce")
     ap.add_argument("--graph", action="store_true", help="multi-GPU fused path: replay the step as a CUDA graph")
     ap.add_argument("--no-fused", action="store_true", help="multi-GPU: NCCL all-to-all instead of the fused NVLink scatter")
+    ap.add_argument("--bwd", action="store_true", help="multi-GPU: also time forward + partitioned backward (fwd_bwd key)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     w = WORKLOADS[args.workload]
