@@ -175,3 +175,40 @@ def test_install_retargets_batch_delay_filter(monkeypatch):
     finally:
         gnn_b200.uninstall(gml)
     assert (gml.LSIGF_DB, gml.GraphFilter_DB) == orig
+
+
+@pytest.mark.parametrize("dataType", [np.float64, torch.float64])
+def test_sparse_source_localization_matches_reference_dataset(dataType):
+    """gnn_b200.datasets_sparse.SourceLocalization (sparse mat-vec diffusion) == the reference data class
+    (dataTools.py:472-592, dense matrix powers) for the same numpy seed: signals, labels, splits and the helper methods."""
+    import scipy.sparse as sp
+    from gnn_b200 import datasets_sparse
+    ref_import.import_reference()
+    import alegnn.utils.graphTools as graphTools
+    import alegnn.utils.dataTools as dataTools
+    np.random.seed(3)
+    G = graphTools.Graph("SBM", 30, {"nCommunities": 3, "probIntra": 0.7, "probInter": 0.2})
+    sources = [2, 11, 23]
+
+    class SparseG:                                   # what a large-graph caller would hold: no dense W anywhere
+        N, W = G.N, sp.csr_matrix(G.W)
+
+    sets = []
+    for cls, graph in ((dataTools.SourceLocalization, G), (datasets_sparse.SourceLocalization, SparseG)):
+        np.random.seed(5)
+        d = cls(graph, 20, 6, 7, sources, tMax=9, dataType=dataType)
+        d.expandDims()
+        np.random.seed(6)
+        sets.append((d, d.getSamples("train", 5), d.getSamples("test", [1, 3]), d.getSamples("valid", 2)))
+    (ref, *ref_draws), (mine, *my_draws) = sets
+    num = lambda a: a.numpy() if isinstance(a, torch.Tensor) else np.asarray(a)  # noqa: E731
+    for part in ("train", "valid", "test"):
+        xs, ys = mine.samples[part]["signals"], mine.samples[part]["targets"]
+        xr, yr = ref.samples[part]["signals"], ref.samples[part]["targets"]
+        assert type(xs) is type(xr) and xs.dtype == xr.dtype and ys.dtype == yr.dtype and tuple(xs.shape) == tuple(xr.shape)
+        assert np.abs(num(xs) - num(xr)).max() < 1e-13 and np.array_equal(num(ys), num(yr))
+    for (xa, ya), (xb, yb) in zip(my_draws, ref_draws):
+        assert tuple(xa.shape) == tuple(xb.shape) and np.abs(num(xa) - num(xb)).max() < 1e-13 and np.array_equal(num(ya), num(yb))
+    scores = np.random.default_rng(0).standard_normal((7, 3))
+    yhat = torch.tensor(scores) if dataType is torch.float64 else scores
+    assert float(mine.evaluate(yhat, mine.samples["test"]["targets"])) == float(ref.evaluate(yhat, ref.samples["test"]["targets"]))
