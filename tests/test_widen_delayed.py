@@ -131,7 +131,6 @@ def test_product_path_is_loud_on_cpu():
 
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
-@pytest.mark.first_gpu_run
 @pytest.mark.parametrize("tag", TAGS)
 @pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-11), (torch.float32, 1e-4)])
 def test_gpu_lsigf_db_matches_reference_fixtures(tag, dtype, tol):
@@ -139,14 +138,12 @@ def test_gpu_lsigf_db_matches_reference_fixtures(tag, dtype, tol):
 
 
 @pytest.mark.gpu
-@pytest.mark.first_gpu_run
 @pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-11), (torch.float32, 1e-4)])
 def test_gpu_graphfilter_db_layer(dtype, tol):
     _check_layer(dtype, "cuda", tol)
 
 
 @pytest.mark.gpu
-@pytest.mark.first_gpu_run
 def test_gpu_flocking_sized_batch_against_batched_matmul():
     """B = 20 trajectories x T = 60 steps x N = 50 agents (the reference's flocking setup, 60 000 space-time nodes):
     compared with the reference's own formulation — per-(b, t) dense products with a unit delay — done with

@@ -8,7 +8,6 @@ from test_distributed import _run
 
 
 @pytest.mark.gpu
-@pytest.mark.first_gpu_run
 @pytest.mark.parametrize("mode,G", [("nodes", 6), ("features", 6), ("features", 16)])
 @pytest.mark.parametrize("dtype_name,tol", [("float32", 1e-4), ("float64", 1e-11)])
 def test_partitioned_backward_nccl_world2(mode, G, dtype_name, tol):

@@ -122,7 +122,6 @@ def test_seeded_construction_matches_reference_init():
 
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
-@pytest.mark.first_gpu_run
 @pytest.mark.parametrize("tag", TAGS)
 @pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 1e-4)])
 def test_gpu_recurrent_layers_match_reference_fixtures(tag, dtype, tol):
@@ -130,7 +129,6 @@ def test_gpu_recurrent_layers_match_reference_fixtures(tag, dtype, tol):
 
 
 @pytest.mark.gpu
-@pytest.mark.first_gpu_run
 def test_gpu_recursion_on_sparse_gso_at_scale():
     """N = 200k (no dense GSO possible): with zero hidden-to-hidden taps and an identity nonlinearity the trajectory
     is A(S) x_t; with non-zero taps it must agree with the recursion unrolled by hand from single LSIGF calls."""

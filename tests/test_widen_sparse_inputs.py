@@ -8,7 +8,6 @@ import lsigf_oracle as orc
 
 
 @pytest.mark.gpu
-@pytest.mark.first_gpu_run
 @pytest.mark.filterwarnings("ignore:Sparse")
 @pytest.mark.parametrize("layout", ["coo", "csr"])
 @pytest.mark.parametrize("where", ["cuda", "cpu"])

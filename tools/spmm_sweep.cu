@@ -18,7 +18,7 @@ using namespace b200gf;
 
 struct Problem {
   int64_t N; int C; int64_t nnz;
-  int64_t* rowptr; int32_t* col; float* val; float* src; float* dst; float* ref;
+  int64_t* rowptr; int32_t* rowptr32; int32_t* col; float* val; float* src; float* dst; float* ref;
   int sm_count;
   double bytes;
 };
@@ -67,6 +67,88 @@ double run(const Problem& P, const char* name, int reps, double peak, int blocks
          P.bytes / (avg * 1e-3) / 1e9 / peak, maxdiff);
   fflush(stdout);
   return avg;
+}
+
+
+template <typename KernT, typename LaunchT>
+double time_variant(const Problem& P, const char* name, int reps, double peak, KernT kern, int threads, size_t smem,
+                    int blocks_per_sm_cap, int64_t max_blocks, LaunchT launch) {
+  cudaFuncAttributes fa;
+  if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncGetAttributes(&fa, kern));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+  int use = blocks_per_sm_cap > 0 ? std::min(blocks_per_sm_cap, occ) : occ;
+  int64_t blocks = std::min<int64_t>(max_blocks, (int64_t)P.sm_count * use);
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaMemset(P.dst, 0xff, (size_t)P.N * P.C * 4));
+  for (int i = 0; i < 2; ++i) launch((unsigned)blocks);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  float best = 1e30f, sum = 0;
+  for (int i = 0; i < reps; ++i) {
+    CK(cudaEventRecord(e0));
+    launch((unsigned)blocks);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    best = std::min(best, ms); sum += ms;
+  }
+  // full comparison against the reference variant's output
+  std::vector<float> a((size_t)P.N * P.C), b((size_t)P.N * P.C);
+  CK(cudaMemcpy(a.data(), P.dst, a.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(b.data(), P.ref, b.size() * 4, cudaMemcpyDeviceToHost));
+  double maxdiff = 0;
+  for (size_t i = 0; i < a.size(); ++i) {
+    double d = fabs((double)a[i] - (double)b[i]);
+    if (!(d <= maxdiff)) maxdiff = d;   // NaN-propagating
+  }
+  const double avg = sum / reps;
+  printf("%-34s regs=%3d smem=%6zu occ=%2d use=%2d blocks=%6lld  avg %.3f ms  best %.3f ms  %.0f GB/s  frac %.3f  maxdiff(all) %.2e\n",
+         name, fa.numRegs, smem, occ, use, (long long)blocks, avg, best, P.bytes / (avg * 1e-3) / 1e9,
+         P.bytes / (avg * 1e-3) / 1e9 / peak, maxdiff);
+  fflush(stdout);
+  return avg;
+}
+
+template <int L, int U, int THREADS, int MINB, int HINT>
+double run_v2w(const Problem& P, const char* name, int reps, double peak) {   // 256-bit loads (VEC = 8)
+  const int n_chunks = (P.C + L * 8 - 1) / (L * 8);
+  const int64_t maxb = ((int64_t)P.N + THREADS / 32 - 1) / (THREADS / 32);
+  auto kern = spmm_hop_v2_kernel<float, int32_t, 8, L, U, THREADS, MINB, HINT, false>;
+  return time_variant(P, name, reps, peak, kern, THREADS, 0, 0, maxb, [&](unsigned blocks) {
+    kern<<<dim3(blocks, n_chunks), THREADS>>>(P.rowptr32, P.col, P.val, P.src, P.C, P.dst, P.C, (int)P.N, P.C, ScatterParam<float, false>{});
+  });
+}
+
+template <int L, int U, int THREADS, int MINB, int HINT, bool I32>
+double run_v2(const Problem& P, const char* name, int reps, double peak) {
+  const int n_chunks = (P.C + L * 4 - 1) / (L * 4);
+  const int64_t maxb = ((int64_t)P.N + THREADS / 32 - 1) / (THREADS / 32);
+  if constexpr (I32) {
+    auto kern = spmm_hop_v2_kernel<float, int32_t, 4, L, U, THREADS, MINB, HINT, false>;
+    return time_variant(P, name, reps, peak, kern, THREADS, 0, 0, maxb, [&](unsigned blocks) {
+      kern<<<dim3(blocks, n_chunks), THREADS>>>(P.rowptr32, P.col, P.val, P.src, P.C, P.dst, P.C, (int)P.N, P.C, ScatterParam<float, false>{});
+    });
+  } else {
+    auto kern = spmm_hop_v2_kernel<float, int64_t, 4, L, U, THREADS, MINB, HINT, false>;
+    return time_variant(P, name, reps, peak, kern, THREADS, 0, 0, maxb, [&](unsigned blocks) {
+      kern<<<dim3(blocks, n_chunks), THREADS>>>(P.rowptr, P.col, P.val, P.src, P.C, P.dst, P.C, (int)P.N, P.C, ScatterParam<float, false>{});
+    });
+  }
+}
+
+template <int L, int SLOTS, int THREADS, int MINB, int HINT>
+double run_async(const Problem& P, const char* name, int reps, double peak) {
+  const int n_chunks = (P.C + L * 4 - 1) / (L * 4);
+  const size_t smem = (size_t)(THREADS / 32) * 2 * SLOTS * L * 16;
+  const int64_t nblk = (P.N + 31) / 32;
+  const int64_t maxb = (nblk + THREADS / 32 - 1) / (THREADS / 32);
+  auto kern = spmm_hop_async_kernel<float, int32_t, 4, L, SLOTS, THREADS, MINB, HINT, false>;
+  return time_variant(P, name, reps, peak, kern, THREADS, smem, 0, maxb, [&](unsigned blocks) {
+    kern<<<dim3(blocks, n_chunks), THREADS, smem>>>(P.rowptr32, P.col, P.val, P.src, P.C, P.dst, P.C, (int)P.N, P.C, ScatterParam<float, false>{});
+  });
 }
 
 // multi-row-per-warp kernel for narrow rows
@@ -135,9 +217,10 @@ int main(int argc, char** argv) {
 
   Problem P;
   P.N = N; P.C = C; P.nnz = nnz; P.sm_count = prop.multiProcessorCount;
-  CK(cudaMalloc(&P.rowptr, (N + 1) * 8)); CK(cudaMalloc(&P.col, nnz * 4)); CK(cudaMalloc(&P.val, nnz * 4));
+  CK(cudaMalloc(&P.rowptr, (N + 1) * 8)); CK(cudaMalloc(&P.rowptr32, (N + 1) * 4)); CK(cudaMalloc(&P.col, nnz * 4)); CK(cudaMalloc(&P.val, nnz * 4));
   CK(cudaMalloc(&P.src, (size_t)N * C * 4)); CK(cudaMalloc(&P.dst, (size_t)N * C * 4)); CK(cudaMalloc(&P.ref, (size_t)N * C * 4));
   CK(cudaMemcpy(P.rowptr, rowptr.data(), (N + 1) * 8, cudaMemcpyHostToDevice));
+  { std::vector<int32_t> r32(rowptr.begin(), rowptr.end()); CK(cudaMemcpy(P.rowptr32, r32.data(), (N + 1) * 4, cudaMemcpyHostToDevice)); }
   CK(cudaMemcpy(P.col, col.data(), nnz * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(P.val, val.data(), nnz * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(P.src, x.data(), (size_t)N * C * 4, cudaMemcpyHostToDevice));
@@ -187,6 +270,33 @@ int main(int argc, char** argv) {
     ADDMR("mrow L8 GS16 U2 EL mb8",    8, 16, 2, 8, 3);
     ADDMR("mrow L8 GS32 U4 EL mb6",    8, 32, 4, 6, 3);
     ADDMR("mrow L8 GS16 U2 ldg mb6",   8, 16, 2, 6, 0);
+  } else if (C <= 64 && getenv("SWEEP_R2")) {
+#define ADDV2(NAME, ...) vs.push_back(V{NAME, [&](bool) { return run_v2<__VA_ARGS__>(P, NAME, reps, peak); }, {0, 0, 0}})
+#define ADDAS(NAME, ...) vs.push_back(V{NAME, [&](bool) { return run_async<__VA_ARGS__>(P, NAME, reps, peak); }, {0, 0, 0}})
+    ADD("r1 shipped (EL noPF mb6)",    16, 4, 256, 6, 3, false);
+    //                                  L  U  THR MINB HINT I32
+    ADDV2("v2 i64 U4 mb6",             16, 4, 256, 6, 3, false);
+    ADDV2("v2 i32 U4 mb6",             16, 4, 256, 6, 3, true);
+    ADDV2("v2 i32 U4 mb5",             16, 4, 256, 5, 3, true);
+    ADDV2("v2 i32 U4 mb7",             16, 4, 256, 7, 3, true);
+    ADDV2("v2 i32 U2 mb8",             16, 2, 256, 8, 3, true);
+    ADDV2("v2 i32 U6 mb5",             16, 6, 256, 5, 3, true);
+    ADDV2("v2 i32 U8 mb4",             16, 8, 256, 4, 3, true);
+    ADDV2("v2 i32 U4 mb6 noEL",        16, 4, 256, 6, 1, true);
+#define ADDV2W(NAME, ...) vs.push_back(V{NAME, [&](bool) { return run_v2w<__VA_ARGS__>(P, NAME, reps, peak); }, {0, 0, 0}})
+    ADDV2W("v2 ldg256 L8 U2 mb6",       8, 2, 256, 6, 3);
+    ADDV2W("v2 ldg256 L8 U2 mb8",       8, 2, 256, 8, 3);
+    ADDV2W("v2 ldg256 L8 U3 mb5",       8, 3, 256, 5, 3);
+    ADDV2W("v2 ldg256 L8 U4 mb4",       8, 4, 256, 4, 3);
+    ADDV2W("v2 ldg256 L8 U1 mb8",       8, 1, 256, 8, 3);
+    //                                  L SLOTS THR MINB HINT
+    ADDAS("async S32 t128 mb3 EL",     16, 32, 128, 3, 3);
+    ADDAS("async S32 t256 mb1 EL",     16, 32, 256, 1, 3);
+    ADDAS("async S32 t128 mb3 noEL",   16, 32, 128, 3, 1);
+    ADDAS("async S64 t128 mb1 EL",     16, 64, 128, 1, 3);
+    ADDAS("async S64 t96  mb2 EL",     16, 64, 96, 2, 3);
+    ADDAS("async S32 t64  mb6 EL",     16, 32, 64, 6, 3);
+    ADDAS("async S32 t128 mb2 EL",     16, 32, 128, 2, 3);
   } else if (C <= 64) {
     ADD("noalloc PF   mb6",            16, 4, 256, 6, 1, true);
     ADDMR("mrow L16 GS32 U2 EL mb6",   16, 32, 2, 6, 3);
