@@ -25,6 +25,7 @@ namespace b200gf {
 
 struct CsrDev {
   int64_t* rowptr = nullptr;  // [n_rows + 1]
+  int32_t* rowptr32 = nullptr;  // the same offsets as int32 when nnz < 2^31 (hop kernel v2: 32-bit index math), else null
   int32_t* col = nullptr;     // [nnz]
   void* val = nullptr;        // [nnz] of dtype
   int64_t nnz = 0;

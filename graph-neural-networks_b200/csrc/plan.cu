@@ -71,6 +71,16 @@ int upload(const HostCsr& A, int64_t n_rows, size_t es, CsrDev& D) {
   if (cudaMalloc(&D.col, (size_t)(nnz + 1) * sizeof(int32_t)) != cudaSuccess) return B200GF_ENOMEM;
   if (cudaMalloc(&D.val, (size_t)(nnz + 1) * es) != cudaSuccess) return B200GF_ENOMEM;
   CUDA_TRY(cudaMemcpy(D.rowptr, A.rowptr.data(), (size_t)(n_rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
+  if (nnz < (int64_t)INT32_MAX) {   // 32-bit copy of the offsets for the hop kernel's 32-bit index arithmetic
+    std::vector<int32_t> r32;
+    try {
+      r32.assign(A.rowptr.begin(), A.rowptr.end());
+    } catch (const std::bad_alloc&) {
+      return B200GF_ENOMEM;
+    }
+    if (cudaMalloc(&D.rowptr32, (size_t)(n_rows + 1) * sizeof(int32_t)) != cudaSuccess) return B200GF_ENOMEM;
+    CUDA_TRY(cudaMemcpy(D.rowptr32, r32.data(), (size_t)(n_rows + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
   if (nnz > 0) {
     CUDA_TRY(cudaMemcpy(D.col, A.col.data(), (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(D.val, A.val.data(), (size_t)nnz * es, cudaMemcpyHostToDevice));
@@ -103,12 +113,20 @@ int init_device(b200gf_plan* p, int device) {
   return B200GF_OK;
 }
 
+// restores the caller's current device when a plan_create call returns (plan_destroy does the same by hand)
+struct DeviceGuard {
+  int prev = -1;
+  DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; (void)cudaGetLastError(); } }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 void free_csr(CsrDev& D) {
   if (!D.owned) return;
   if (D.rowptr) cudaFree(D.rowptr);
+  if (D.rowptr32) cudaFree(D.rowptr32);
   if (D.col) cudaFree(D.col);
   if (D.val) cudaFree(D.val);
-  D.rowptr = nullptr; D.col = nullptr; D.val = nullptr;
+  D.rowptr = nullptr; D.rowptr32 = nullptr; D.col = nullptr; D.val = nullptr;
 }
 
 }  // namespace
@@ -154,6 +172,7 @@ int b200gf_plan_create(b200gf_plan** out, int device, int64_t N, int E, const in
   if (dtype != B200GF_F32 && dtype != B200GF_F64) return B200GF_EUNSUPPORTED;
   if (N > (int64_t)INT32_MAX) return B200GF_EUNSUPPORTED;
   *out = nullptr;
+  DeviceGuard guard;   // init_device() switches to the plan's device; the caller's current device is restored on return
   b200gf_plan* p = new (std::nothrow) b200gf_plan();
   if (!p) return B200GF_ENOMEM;
   int rc = init_device(p, device);
@@ -190,6 +209,7 @@ int b200gf_plan_create_ops(b200gf_plan** out, int device, int64_t n_rows, int64_
   if (dtype != B200GF_F32 && dtype != B200GF_F64) return B200GF_EUNSUPPORTED;
   if (n_cols > (int64_t)INT32_MAX) return B200GF_EUNSUPPORTED;
   *out = nullptr;
+  DeviceGuard guard;   // init_device() switches to the plan's device; the caller's current device is restored on return
   b200gf_plan* p = new (std::nothrow) b200gf_plan();
   if (!p) return B200GF_ENOMEM;
   int rc = init_device(p, device);

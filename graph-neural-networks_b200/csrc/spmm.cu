@@ -15,6 +15,14 @@
 #include "common.cuh"
 #include "spmm_kernels.cuh"
 
+// L2 policy of the gathered rows in the v2 kernel (spmm_kernels.cuh HINT codes), chosen from profiles/r2_spmm_sweep2_c64.log
+#ifndef B200GF_HOP_L2_HINT
+#define B200GF_HOP_L2_HINT 3
+#endif
+#ifndef B200GF_HOP_L2_FRAC
+#define B200GF_HOP_L2_FRAC 1.0f
+#endif
+
 namespace b200gf {
 
 template <typename T>
@@ -75,6 +83,42 @@ static int launch_multirow(int sm_count, const CsrDev& A, int64_t n_rows, const 
   return B200GF_OK;
 }
 
+// Round-2 kernel (spmm_kernels.cuh: spmm_hop_v2_kernel): 32-byte lanes (LDG.E.256), 32-bit index arithmetic, no spills.
+// L lanes x 32 bytes cover a row chunk; 32/L neighbours per warp-wide load, U loads in flight per lane; 4 blocks of 256
+// threads per SM (64 registers); column chunks on blockIdx.y.  Sweep: profiles/r2_spmm_sweep*.log.
+template <typename T, int L, bool SCATTER>
+static int launch_v2(int sm_count, const CsrDev& A, int64_t n_rows, const T* src, int64_t src_ld, T* dst, int64_t dst_ld,
+                     int C, cudaStream_t st, const ScatterHost* sh) {
+  constexpr int VEC = 32 / sizeof(T), U = 4, THREADS = 256, MINB = sizeof(T) == 4 ? 4 : 3, HINT = B200GF_HOP_L2_HINT;
+  auto kern = spmm_hop_v2_kernel<T, int32_t, VEC, L, U, THREADS, MINB, HINT, SCATTER>;
+  if (n_rows == 0) return B200GF_OK;
+  const int n_chunks = (C + L * VEC - 1) / (L * VEC);
+  if (n_chunks > 65535) return B200GF_EUNSUPPORTED;
+  const int wpb = THREADS / 32;
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, 0));
+  if (occ < 1) occ = 1;
+  int64_t blocks = (n_rows + wpb - 1) / wpb;
+  // one resident wave per chunk when there is a single chunk; with several chunks each chunk gets its own wave-sized
+  // slice of the grid so that the block scheduler runs them chunk-major
+  const int64_t cap = (int64_t)sm_count * occ;
+  if (blocks > cap) blocks = cap;
+  ScatterParam<T, SCATTER> sp{};
+  if constexpr (SCATTER) sp.a = make_scatter<T>(sh);
+  kern<<<dim3((unsigned)blocks, (unsigned)n_chunks), THREADS, 0, st>>>(A.rowptr32, A.col, reinterpret_cast<const T*>(A.val),
+                                                                      src, (int)src_ld, dst, (int)dst_ld, (int)n_rows, C,
+                                                                      B200GF_HOP_L2_FRAC, sp);
+  LAUNCH_CHECK();
+  return B200GF_OK;
+}
+
+template <typename T, int L>
+static int launch_v2_sc(int sm_count, const CsrDev& A, int64_t n_rows, const T* src, int64_t src_ld, T* dst,
+                        int64_t dst_ld, int C, cudaStream_t st, const ScatterHost* sh) {
+  if (sh && sh->n_peers > 0) return launch_v2<T, L, true>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);
+  return launch_v2<T, L, false>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, nullptr);
+}
+
 template <typename T>
 static int launch_typed(int sm_count, const CsrDev& A, int64_t n_rows, const void* src_, int64_t src_ld,
                         void* dst_, int64_t dst_ld, int C, cudaStream_t st, const ScatterHost* sh) {
@@ -96,6 +140,20 @@ static int launch_typed(int sm_count, const CsrDev& A, int64_t n_rows, const voi
   if (nv <= 2) return launch_multirow<T, VEC, 2, 8, 2, MB>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);
   if (nv <= 4) return launch_multirow<T, VEC, 4, 16, 2, sizeof(T) == 4 ? 8 : 4>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);
   if (nv <= 8) return launch_multirow<T, VEC, 8, 32, 4, MB>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);
+  // rows wider than 128 bytes: the v2 kernel when its preconditions hold (32-byte aligned rows, 32-bit offsets)
+  constexpr int VW = 32 / sizeof(T);
+  const int Cw = (C + VW - 1) / VW * VW;
+  bool wide_ok = A.rowptr32 != nullptr && (src_ld % VW == 0) && (dst_ld % VW == 0) && (Cw <= src_ld) && (Cw <= dst_ld) &&
+                 ((reinterpret_cast<uintptr_t>(src) & 31) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) &&
+                 src_ld <= INT32_MAX && dst_ld <= INT32_MAX && n_rows <= INT32_MAX;
+  if (sh && sh->n_peers > 0)
+    wide_ok = wide_ok && sh->gl % VW == 0 && sh->out_ld % VW == 0 && sh->out_col % VW == 0 && sh->stride_b % VW == 0;
+  if (wide_ok) {
+    const int nw = Cw / VW;  // 32-byte vectors per row
+    if (nw <= 8) return launch_v2_sc<T, 8>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);
+    if (nw <= 16) return launch_v2_sc<T, 16>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);
+    return launch_v2_sc<T, 32>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);
+  }
   if (nv <= 16) return launch_one<T, VEC, 16, 4>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);
   return launch_one<T, VEC, 32, 4>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);
 }

@@ -41,7 +41,7 @@ __device__ __forceinline__ uint64_t evict_last_policy(float frac) {
 template <typename T, int VEC, int HINT>
 __device__ __forceinline__ Acc<T, VEC> load_vec(const T* p, uint64_t pol) {
   Acc<T, VEC> a;
-  if constexpr (VEC == 4) {
+  if constexpr (VEC == 4 && sizeof(T) == 4) {
     float4 t;
     if constexpr (HINT == 0) {
       t = __ldg(reinterpret_cast<const float4*>(p));
@@ -53,19 +53,36 @@ __device__ __forceinline__ Acc<T, VEC> load_vec(const T* p, uint64_t pol) {
                    : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "l"(p), "l"(pol));
     }
     a.v[0] = t.x; a.v[1] = t.y; a.v[2] = t.z; a.v[3] = t.w;
-  } else if constexpr (VEC == 8) {
-    // sm_100 256-bit load (LDG.E.256): one lane fetches a whole 32-byte sector; L2::evict_last is a plain qualifier
-    // here (no policy register).  HINT 0/1: no_allocate only.
-    static_assert(sizeof(T) == 4, "v8 loads are for 4-byte elements");
-    unsigned r[8];
-    if constexpr (HINT >= 2)
-      asm volatile("ld.global.nc.L1::no_allocate.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
-    else
-      asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+  } else if constexpr (VEC * sizeof(T) == 32) {
+    // sm_100 256-bit load (LDG.E.256): one lane fetches a whole 32-byte sector.  HINT 0/1: L1::no_allocate only;
+    // HINT 3: L2::evict_last as a plain qualifier (no policy register); other HINTs: the policy in `pol`.
+    if constexpr (sizeof(T) == 4) {
+      unsigned r[8];
+      if constexpr (HINT == 3)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+      else if constexpr (HINT >= 2)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p), "l"(pol));
+      else
+        asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a.v[i] = __uint_as_float(r[i]);
+      for (int i = 0; i < 8; ++i) a.v[i] = __uint_as_float(r[i]);
+    } else {
+      double d[4];
+      if constexpr (HINT == 3)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_last.v4.b64 {%0,%1,%2,%3}, [%4];"
+                     : "=d"(d[0]), "=d"(d[1]), "=d"(d[2]), "=d"(d[3]) : "l"(p));
+      else if constexpr (HINT >= 2)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.b64 {%0,%1,%2,%3}, [%4], %5;"
+                     : "=d"(d[0]), "=d"(d[1]), "=d"(d[2]), "=d"(d[3]) : "l"(p), "l"(pol));
+      else
+        asm volatile("ld.global.nc.L1::no_allocate.v4.b64 {%0,%1,%2,%3}, [%4];"
+                     : "=d"(d[0]), "=d"(d[1]), "=d"(d[2]), "=d"(d[3]) : "l"(p));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a.v[i] = d[i];
+    }
   } else if constexpr (VEC == 2) {
     double2 t;
     if constexpr (HINT == 0) {
@@ -86,9 +103,22 @@ __device__ __forceinline__ Acc<T, VEC> load_vec(const T* p, uint64_t pol) {
 // SH 0: default store   1: st.global.cs (streaming: the result row is not re-read by this kernel)
 template <typename T, int VEC, int SH>
 __device__ __forceinline__ void store_vec(T* p, const Acc<T, VEC>& a) {
-  if constexpr (VEC == 8) {
-    reinterpret_cast<float4*>(p)[0] = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
-    reinterpret_cast<float4*>(p)[1] = make_float4(a.v[4], a.v[5], a.v[6], a.v[7]);
+  if constexpr (VEC * sizeof(T) == 32 && sizeof(T) == 4) {
+    if constexpr (SH == 1) {
+      __stcs(reinterpret_cast<float4*>(p), make_float4(a.v[0], a.v[1], a.v[2], a.v[3]));
+      __stcs(reinterpret_cast<float4*>(p) + 1, make_float4(a.v[4], a.v[5], a.v[6], a.v[7]));
+    } else {
+      reinterpret_cast<float4*>(p)[0] = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+      reinterpret_cast<float4*>(p)[1] = make_float4(a.v[4], a.v[5], a.v[6], a.v[7]);
+    }
+  } else if constexpr (VEC * sizeof(T) == 32) {
+    if constexpr (SH == 1) {
+      __stcs(reinterpret_cast<double2*>(p), make_double2(a.v[0], a.v[1]));
+      __stcs(reinterpret_cast<double2*>(p) + 1, make_double2(a.v[2], a.v[3]));
+    } else {
+      reinterpret_cast<double2*>(p)[0] = make_double2(a.v[0], a.v[1]);
+      reinterpret_cast<double2*>(p)[1] = make_double2(a.v[2], a.v[3]);
+    }
   } else if constexpr (VEC == 4) {
     if constexpr (SH == 1) __stcs(reinterpret_cast<float4*>(p), make_float4(a.v[0], a.v[1], a.v[2], a.v[3]));
     else *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
@@ -263,13 +293,18 @@ struct ScatterParam { ScatterArgs<T> a; };
 template <typename T>
 struct ScatterParam<T, false> {};
 
-template <typename T, typename IDX, int VEC, int L, int U, int THREADS, int MINB, int HINT, bool SCATTER>
+// HINT: 0/1 no L2 policy; 3 evict_last on every gathered line; 2 evict_last on the fraction l2_frac of the lines (by
+// address hash), the rest unchanged; 6 the same with evict_first on the rest.  SH = 1: streaming stores of the result.
+template <typename T, typename IDX, int VEC, int L, int U, int THREADS, int MINB, int HINT, bool SCATTER, int SH = 0>
 __global__ void __launch_bounds__(THREADS, MINB)
 spmm_hop_v2_kernel(const IDX* __restrict__ rowptr, const int32_t* __restrict__ col, const T* __restrict__ val,
                    const T* __restrict__ src, int src_ld, T* __restrict__ dst, int dst_ld, int n_rows, int C,
-                   const ScatterParam<T, SCATTER> sp) {
+                   float l2_frac, const ScatterParam<T, SCATTER> sp) {
   uint64_t pol = 0;
-  if constexpr (HINT >= 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  if constexpr (HINT == 3) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  if constexpr (HINT == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, %1;" : "=l"(pol) : "f"(l2_frac));
+  if constexpr (HINT == 6)
+    asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, %1;" : "=l"(pol) : "f"(l2_frac));
   constexpr int S = 32 / L;
   const int lane = threadIdx.x & 31;
   const int sub = lane / L;
@@ -282,15 +317,15 @@ spmm_hop_v2_kernel(const IDX* __restrict__ rowptr, const int32_t* __restrict__ c
     const bool col_ok = cbase < C;
     const T* __restrict__ srcc = src + cbase;
     for (int row = warp0; row < n_rows;) {
-      const IDX beg = __ldg(rowptr + row);
-      const int len = (int)(__ldg(rowptr + row + 1) - beg);
+      IDX p = __ldg(rowptr + row);
+      const IDX end = __ldg(rowptr + row + 1);
       Acc<T, VEC> acc;
       acc.zero();
-      for (int b0 = 0; b0 < len; b0 += 32) {
+      for (; p < end; p += 32) {
         int32_t c = 0;
         T v = T(0);
-        if (b0 + lane < len) { c = ld_stream(col + beg + b0 + lane); v = ld_stream(val + beg + b0 + lane); }
-        const int cnt = min(len - b0, 32);
+        const int cnt = (int)min((IDX)32, end - p);
+        if (lane < cnt) { c = ld_stream(col + p + lane); v = ld_stream(val + p + lane); }
 #pragma unroll 1
         for (int j = 0; j < cnt; j += S * U) {
           Acc<T, VEC> buf[U];
@@ -322,7 +357,7 @@ spmm_hop_v2_kernel(const IDX* __restrict__ rowptr, const int32_t* __restrict__ c
       asm volatile("mov.u32 %0, %%laneid;" : "=r"(ln));
       asm volatile("mov.u32 %0, %%nctaid.x;" : "=r"(gdx));
       if (ln < (unsigned)L && cbase < C) {
-        store_vec<T, VEC, 0>(dst + (int64_t)row * dst_ld + cbase, acc);
+        store_vec<T, VEC, SH>(dst + (int64_t)row * dst_ld + cbase, acc);
         if constexpr (SCATTER) {
           if (sp.a.n_peers > 0) scatter_store<T, VEC>(sp.a, row, cbase, acc);
         }

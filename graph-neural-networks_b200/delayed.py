@@ -63,6 +63,8 @@ def _plan_for_batch(S):
     if S.device.type != "cuda":
         raise RuntimeError("b200gf: LSIGF_DB needs CUDA tensors (there is no CPU fallback); got GSO on %s" % S.device)
     key = (S.data_ptr(), S._version, tuple(S.shape), tuple(S.stride()), S.dtype, str(S.device))
+    for k in [k for k, h in _CACHE.items() if h[0]() is None]:     # GSO batch already collected: free its plan now
+        del _CACHE[k]
     hit = _CACHE.get(key)
     if hit is not None and hit[0]() is S:
         return hit[1]

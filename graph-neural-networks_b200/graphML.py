@@ -173,6 +173,24 @@ def LSIGF(h, S, x, b=None):
     B = x.shape[0]
     assert x.shape[1] == G                       # graphML.py:139
     assert x.shape[2] == N                       # graphML.py:140
+    if b is not None:
+        # the reference adds b by broadcasting (graphML.py:174-175): GraphFilter passes [F, 1], and the reference's own
+        # GatedGRNN reshapes its biases to (1, F, 1) before calling LSIGF (graphML.py:1394-1404, :1461)
+        if b.dim() == 3 and b.shape[0] == 1:
+            b = b[0]
+        elif b.dim() == 1 and N == 1:
+            b = b.reshape(-1, 1)
+        if not (b.dim() == 2 and b.shape[0] in (1, F_) and b.shape[1] in (1, N)):
+            raise RuntimeError("b200gf: LSIGF bias must broadcast against [B, F, N] as [F, 1], [F, N], [1, F, 1] or "
+                               "[1, F, N]; got %s" % (tuple(b.shape),))
+        if b.shape[0] == 1 and F_ > 1:
+            b = b.expand(F_, b.shape[1])
+    return _dispatch(h, S, x, b)
+
+
+def _dispatch_cuda(h, S, x, b):
+    """Device part of LSIGF: loud checks (there is no CPU path), plan lookup, the autograd function over the C ABI.
+    `_dispatch` is the single hook the CPU tests replace with the oracle to exercise the argument handling above."""
     if x.device.type != "cuda":
         raise RuntimeError("b200gf: LSIGF needs CUDA tensors (there is no CPU fallback); got x on %s" % x.device)
     if x.dtype not in _ENUM:
@@ -180,12 +198,13 @@ def LSIGF(h, S, x, b=None):
     if h.dtype != x.dtype or S.dtype != x.dtype or (b is not None and b.dtype != x.dtype):
         # torch.matmul in the reference raises on mixed dtypes too ("expected scalar type ...")
         raise RuntimeError("b200gf: LSIGF expects h, S, x, b of one dtype, got h=%s S=%s x=%s" % (h.dtype, S.dtype, x.dtype))
-    if b is not None:
-        assert b.dim() == 2 and b.shape[0] == F_ and b.shape[1] in (1, N)
     plan = plan_for(S, x.device)
     if plan.device != x.device and not (plan.device.index == (x.device.index or 0)):
         raise RuntimeError("b200gf: GSO plan lives on %s but x is on %s" % (plan.device, x.device))
     return _LSIGFFunction.apply(h, x, b, plan)
+
+
+_dispatch = _dispatch_cuda
 
 
 class GraphFilter(nn.Module):

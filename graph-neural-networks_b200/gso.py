@@ -218,6 +218,14 @@ _PLAN_CACHE = {}
 _PLAN_CACHE_MAX = 16
 
 
+def _purge_dead_plans():
+    """Drop cache entries whose GSO tensor has been collected, so their device CSR memory is released now rather than
+    when FIFO eviction reaches them (a new dense S every step — edge-failure sampling — would otherwise pin 16 plans)."""
+    dead = [k for k, hit in _PLAN_CACHE.items() if hit[0]() is None]
+    for k in dead:
+        del _PLAN_CACHE[k]
+
+
 def _dense_key(S):
     return (S.data_ptr(), S._version, tuple(S.shape), tuple(S.stride()), S.dtype, str(S.device))
 
@@ -233,6 +241,7 @@ def plan_for(S, device=None):
     if S.requires_grad:
         raise NotImplementedError("b200gf: gradients w.r.t. the GSO are not part of the LSIGF path "
                                   "(the reference keeps S as a plain attribute, graphML.py:2099)")
+    _purge_dead_plans()
     if S.layout != torch.strided:
         # torch sparse GSO (SURVEY §8b extension): never densified — converted once to host CSR, cached per tensor
         assert S.dim() == 3 and S.shape[1] == S.shape[2]

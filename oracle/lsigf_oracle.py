@@ -170,6 +170,80 @@ def lsigf_grads_sparse(h, S_list, x, dy, bias_shape=None):
     return dh, dx, db
 
 
+def threaded_spmm(M):
+    """scipy CSR matrix -> callable X -> M @ X (float64) running on all host cores through torch.sparse (MKL); scipy's own
+    CSR x dense product is single-threaded, which makes the full-size checks (N = 1M, C = 2048) take minutes."""
+    import warnings
+    import torch
+    M = sp.csr_matrix(M)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                      # "sparse CSR support is in beta"
+        Mt = torch.sparse_csr_tensor(torch.from_numpy(M.indptr.astype(np.int64)),
+                                     torch.from_numpy(M.indices.astype(np.int64)),
+                                     torch.from_numpy(M.data.astype(np.float64)), size=M.shape)
+    return lambda X: torch.sparse.mm(Mt, torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64))).numpy()
+
+
+def lsigf_sparse_stream(h, S_list, x, b=None, spmm=None):
+    """lsigf_sparse without materialising z [E,K,N,C]: hop by hop (graphML.py:158-161), each shifted signal contracted
+    with its taps as soon as it exists (graphML.py:170-171 distributes over k).  Same result; memory 3 node-major
+    matrices instead of E*K, BLAS GEMMs instead of an einsum — this is what the full-size GPU parity tests
+    (N = 1M, C = 2048, E = 4) run on the host.  Cross-checked against lsigf_sparse in tests/test_oracle_golden.py."""
+    h = np.asarray(h, dtype=np.float64)
+    F, E, K, G = h.shape
+    x = np.asarray(x, dtype=np.float64)
+    B, _, N = x.shape
+    S_list = _csr_list(S_list)
+    assert len(S_list) == E and x.shape[1] == G
+    X0 = np.ascontiguousarray(x.reshape(B * G, N).T)                       # [N, C], column (b, g) at b*G + g
+    y = np.zeros((N * B, F))
+    for e in range(E):
+        St = S_list[e].T.tocsr()
+        shift = (lambda X, St=St: St @ X) if spmm is None else spmm(St)    # `spmm`: optional threaded M -> (X -> M @ X)
+        cur = X0
+        for k in range(K):
+            if k > 0:
+                cur = shift(cur)                                           # x <- x S_e  (row-vector shift)
+            y += cur.reshape(N * B, G) @ h[:, e, k, :].T
+    y = y.reshape(N, B, F).transpose(1, 2, 0)
+    if b is not None:
+        y = y + np.asarray(b, dtype=np.float64)[None, :, :]
+    return y
+
+
+def lsigf_grads_sparse_stream(h, S_list, x, dy, bias_shape=None, spmm=None):
+    """Streaming form of lsigf_grads_sparse: dh[f,e,k,g] = <dy_f, z_{e,k,g}>, dx = sum_{e,k} (dy S_e^T^k) h."""
+    h = np.asarray(h, dtype=np.float64)
+    x = np.asarray(x, dtype=np.float64)
+    dy = np.asarray(dy, dtype=np.float64)
+    F, E, K, G = h.shape
+    B, _, N = x.shape
+    S_list = _csr_list(S_list)
+    X0 = np.ascontiguousarray(x.reshape(B * G, N).T)                       # [N, B*G]
+    D0 = np.ascontiguousarray(dy.reshape(B * F, N).T)                      # [N, B*F]
+    dh = np.zeros((F, E, K, G))
+    dxn = np.zeros((N * B, G))
+    for e in range(E):
+        St = S_list[e].T.tocsr()
+        Sm = S_list[e].tocsr()
+        fwd = (lambda X, St=St: St @ X) if spmm is None else spmm(St)
+        bwd = (lambda X, Sm=Sm: Sm @ X) if spmm is None else spmm(Sm)
+        z, v = X0, D0
+        for k in range(K):
+            if k > 0:
+                z = fwd(z)                                                 # z_k = z_{k-1} S_e
+                v = bwd(v)                                                 # v_k = v_{k-1} S_e^T
+            dh[:, e, k, :] = D0.reshape(N * B, F).T @ z.reshape(N * B, G)
+            dxn += v.reshape(N * B, F) @ h[:, e, k, :]
+    dx = dxn.reshape(N, B, G).transpose(1, 2, 0)
+    db = None
+    if bias_shape is not None:
+        db = dy.sum(axis=0)
+        if bias_shape[1] == 1:
+            db = db.sum(axis=1, keepdims=True)
+    return dh, dx, db
+
+
 # --------------------------------------------------------------------------------------------
 # dense torch CPU port: the timed CPU baseline (bench.py cpu_baseline / --impl reference)
 # --------------------------------------------------------------------------------------------

@@ -212,3 +212,39 @@ def test_sparse_source_localization_matches_reference_dataset(dataType):
     scores = np.random.default_rng(0).standard_normal((7, 3))
     yhat = torch.tensor(scores) if dataType is torch.float64 else scores
     assert float(mine.evaluate(yhat, mine.samples["test"]["targets"])) == float(ref.evaluate(yhat, ref.samples["test"]["targets"]))
+
+
+def test_reference_gatedgrnn_with_biases_after_install(monkeypatch):
+    """the reference's own GatedGRNN (graphML.py:1292-1527) reshapes its biases to (1, H, 1) before calling
+    the module-global LSIGF (:1394-1404, :1403, :1461).  After install() that call lands in gnn_b200.LSIGF, whose argument
+    handling must accept what the reference's broadcast add accepts.  The dense CPU oracle stands in for the CUDA
+    dispatch (`graphML._dispatch`), so the shape handling of the product function itself is what runs here."""
+    import gnn_b200
+    gml = ref_import.import_reference()
+    seen = []
+
+    def dispatch(h, S, x, b):
+        seen.append(None if b is None else tuple(b.shape))
+        return orc.lsigf_dense_torch(h, S, x, b)
+
+    rng = np.random.default_rng(5)
+    B, T, F, H, N, K, E = 2, 3, 2, 4, 7, 3, 1
+    a = torch.tensor(rng.standard_normal((H, E, K, F)))
+    bt = torch.tensor(rng.standard_normal((H, E, K, H)))
+    S = torch.tensor(orc.random_sparse_gso(rng, N, 3, E))
+    x = torch.tensor(rng.standard_normal((B, T, F, N)))
+    z0 = torch.tensor(rng.standard_normal((B, H, N)))
+    xb, zb = torch.tensor(rng.standard_normal((H, 1))), torch.tensor(rng.standard_normal((H, 1)))
+    want = gml.GatedGRNN(a, bt, S, x, z0, torch.tanh, xBias=xb, zBias=zb)
+    try:
+        gnn_b200.install(gml)
+        monkeypatch.setattr(gnn_b200.graphML, "_dispatch", dispatch)
+        got = gml.GatedGRNN(a, bt, S, x, z0, torch.tanh, xBias=xb, zBias=zb)
+    finally:
+        gnn_b200.uninstall(gml)
+    assert seen and all(s == (H, 1) for s in seen)          # (1, H, 1) was normalised to the [F, 1] the C ABI takes
+    for w, g in zip(want, got):
+        assert _rel(g.detach().numpy(), w.detach().numpy()) < 1e-12
+    # shapes the reference's broadcast would reject are still rejected loudly
+    with pytest.raises(RuntimeError, match="bias must broadcast"):
+        gnn_b200.LSIGF(a, S, x[:, 0], torch.zeros(H + 1, 1, dtype=torch.float64))

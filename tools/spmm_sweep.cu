@@ -112,13 +112,13 @@ double time_variant(const Problem& P, const char* name, int reps, double peak, K
   return avg;
 }
 
-template <int L, int U, int THREADS, int MINB, int HINT>
-double run_v2w(const Problem& P, const char* name, int reps, double peak) {   // 256-bit loads (VEC = 8)
+template <int L, int U, int THREADS, int MINB, int HINT, int SH = 0>
+double run_v2w(const Problem& P, const char* name, int reps, double peak, float frac = 1.0f) {   // 256-bit loads (VEC = 8)
   const int n_chunks = (P.C + L * 8 - 1) / (L * 8);
   const int64_t maxb = ((int64_t)P.N + THREADS / 32 - 1) / (THREADS / 32);
-  auto kern = spmm_hop_v2_kernel<float, int32_t, 8, L, U, THREADS, MINB, HINT, false>;
+  auto kern = spmm_hop_v2_kernel<float, int32_t, 8, L, U, THREADS, MINB, HINT, false, SH>;
   return time_variant(P, name, reps, peak, kern, THREADS, 0, 0, maxb, [&](unsigned blocks) {
-    kern<<<dim3(blocks, n_chunks), THREADS>>>(P.rowptr32, P.col, P.val, P.src, P.C, P.dst, P.C, (int)P.N, P.C, ScatterParam<float, false>{});
+    kern<<<dim3(blocks, n_chunks), THREADS>>>(P.rowptr32, P.col, P.val, P.src, P.C, P.dst, P.C, (int)P.N, P.C, frac, ScatterParam<float, false>{});
   });
 }
 
@@ -129,12 +129,12 @@ double run_v2(const Problem& P, const char* name, int reps, double peak) {
   if constexpr (I32) {
     auto kern = spmm_hop_v2_kernel<float, int32_t, 4, L, U, THREADS, MINB, HINT, false>;
     return time_variant(P, name, reps, peak, kern, THREADS, 0, 0, maxb, [&](unsigned blocks) {
-      kern<<<dim3(blocks, n_chunks), THREADS>>>(P.rowptr32, P.col, P.val, P.src, P.C, P.dst, P.C, (int)P.N, P.C, ScatterParam<float, false>{});
+      kern<<<dim3(blocks, n_chunks), THREADS>>>(P.rowptr32, P.col, P.val, P.src, P.C, P.dst, P.C, (int)P.N, P.C, 1.0f, ScatterParam<float, false>{});
     });
   } else {
     auto kern = spmm_hop_v2_kernel<float, int64_t, 4, L, U, THREADS, MINB, HINT, false>;
     return time_variant(P, name, reps, peak, kern, THREADS, 0, 0, maxb, [&](unsigned blocks) {
-      kern<<<dim3(blocks, n_chunks), THREADS>>>(P.rowptr, P.col, P.val, P.src, P.C, P.dst, P.C, (int)P.N, P.C, ScatterParam<float, false>{});
+      kern<<<dim3(blocks, n_chunks), THREADS>>>(P.rowptr, P.col, P.val, P.src, P.C, P.dst, P.C, (int)P.N, P.C, 1.0f, ScatterParam<float, false>{});
     });
   }
 }
@@ -270,6 +270,29 @@ int main(int argc, char** argv) {
     ADDMR("mrow L8 GS16 U2 EL mb8",    8, 16, 2, 8, 3);
     ADDMR("mrow L8 GS32 U4 EL mb6",    8, 32, 4, 6, 3);
     ADDMR("mrow L8 GS16 U2 ldg mb6",   8, 16, 2, 6, 0);
+  } else if (C <= 64 && getenv("SWEEP_R2") && atoi(getenv("SWEEP_R2")) == 2) {
+#define ADDW(NAME, FRAC, ...) vs.push_back(V{NAME, [&](bool) { return run_v2w<__VA_ARGS__>(P, NAME, reps, peak, FRAC); }, {0, 0, 0}})
+    ADD("r1 shipped (EL noPF mb6)",    16, 4, 256, 6, 3, false);
+    //                                 L  U  THR MINB HINT SH
+    ADDW("w U4 mb4 EL all",        1.0f,  8, 4, 256, 4, 3);
+    ADDW("w U1 mb8 EL all",        1.0f,  8, 1, 256, 8, 3);
+    ADDW("w U2 mb8 EL all",        1.0f,  8, 2, 256, 8, 3);
+    ADDW("w U4 mb4 EL all st.cs",  1.0f,  8, 4, 256, 4, 3, 1);
+    ADDW("w U4 mb4 noEL",          1.0f,  8, 4, 256, 4, 1);
+    ADDW("w U4 mb4 ELf .25",       0.25f, 8, 4, 256, 4, 2);
+    ADDW("w U4 mb4 ELf .35",       0.35f, 8, 4, 256, 4, 2);
+    ADDW("w U4 mb4 ELf .45",       0.45f, 8, 4, 256, 4, 2);
+    ADDW("w U4 mb4 ELf .60",       0.60f, 8, 4, 256, 4, 2);
+    ADDW("w U4 mb4 ELf/EF .25",    0.25f, 8, 4, 256, 4, 6);
+    ADDW("w U4 mb4 ELf/EF .35",    0.35f, 8, 4, 256, 4, 6);
+    ADDW("w U4 mb4 ELf/EF .45",    0.45f, 8, 4, 256, 4, 6);
+    ADDW("w U4 mb4 ELf/EF .60",    0.60f, 8, 4, 256, 4, 6);
+    ADDW("w U4 mb4 ELf/EF .35 cs", 0.35f, 8, 4, 256, 4, 6, 1);
+    ADDW("w U1 mb8 ELf/EF .35",    0.35f, 8, 1, 256, 8, 6);
+    ADDW("w U4 t128 mb8 EL all",   1.0f,  8, 4, 128, 8, 3);
+    ADDW("w U2 t128 mb12 EL all",  1.0f,  8, 2, 128, 12, 3);
+    ADDW("w U8 mb2 EL all",        1.0f,  8, 8, 256, 2, 3);
+    ADDW("w U6 mb3 EL all",        1.0f,  8, 6, 256, 3, 3);
   } else if (C <= 64 && getenv("SWEEP_R2")) {
 #define ADDV2(NAME, ...) vs.push_back(V{NAME, [&](bool) { return run_v2<__VA_ARGS__>(P, NAME, reps, peak); }, {0, 0, 0}})
 #define ADDAS(NAME, ...) vs.push_back(V{NAME, [&](bool) { return run_async<__VA_ARGS__>(P, NAME, reps, peak); }, {0, 0, 0}})
