@@ -1,19 +1,27 @@
 #!/usr/bin/env python
-"""bench.py — LSIGF edge·feature ops/s on B200 (BASELINE.json `metric`), with roofline and CPU baseline.
+"""bench.py — LSIGF edge·feature ops/s on B200 (BASELINE.json `metric`), with roofline, parity check and CPU baseline.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload er1m|cfg2|cfg3|cfg4|er2m] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload er1m|cfg2|cfg3|cfg4|er2m|sbm1m] [--impl reference]
 
 A "step" is one LSIGF forward (alegnn/utils/graphML.py:83-176 semantics) over one synthetic batch:
   value  = E * nnz * (K-1) * B * G / t_step     (one op = one multiply-add of one non-zero of S with one feature
-           column for one hop), inputs resident in HBM in the reference's [B,G,N] layout, timed with
-           CUDA events around exactly K steps after a barrier + synchronize, max over ranks.
-  e2e    = same metric through the public API (gnn_b200.LSIGF) with pinned HOST x and y: every step's H2D and D2H copy
-           inside the timed region, overlapped ACROSS steps on two copy streams (class E2EPipeline).
-  roofline = the shift kernel (spmm_hop_kernel): algorithmic bytes per launch (gather model) divided by
-           its average duration measured live with CUDA events around every hop launch inside the timed region
-           (events recorded by the library on the launching stream), against MEASURED_PEAKS.json's HBM copy bandwidth.
+           column for one hop), inputs resident in HBM, timed with CUDA events around exactly K steps
+           after a barrier + synchronize, max over ranks.  N = 1: x in the reference's [B,G,N] layout, the layout
+           conversion is inside the step.  N > 1: every rank holds its shard of the node-major x.
+  e2e    = same metric through the public API with pinned HOST x and y: every step's H2D and D2H copy inside the
+           timed region, overlapped ACROSS steps on two copy streams (class E2EPipeline).
+  roofline = the shift kernel: algorithmic bytes per launch (gather model) divided by its average
+           duration measured live with CUDA events around every hop launch inside the timed region (events recorded
+           by the library on the launching stream), against MEASURED_PEAKS.json's HBM copy bandwidth.
+  parity_max_rel = max|y - y_ref| / max|y_ref| of the timed path's output against the fp64 CPU oracle
+           (oracle/lsigf_oracle.py:lsigf_sparse_stream) at the FULL workload size, at every N (the ranks' rows are
+           gathered); the run fails above 1e-4.  `selftest` (N > 1): forward AND backward of both shardings against the
+           oracle on a small graph, over NCCL / NVLink on the same ranks.
   cpu_baseline = the reference's dense torch.matmul algorithm (oracle/lsigf_oracle.py:lsigf_dense_torch, a port: the
-           reference is Python and cannot travel to the GPU box) on this box's host cores, bounded sample.
+           reference is Python, cannot be pip-installed offline — DESIGN.md §6 — and cannot travel to the GPU box) on this
+           box's host cores, bounded sample, thread count pinned and printed.
+  configs = at N = 1 the other single-GPU configurations of BASELINE.json (cfg2, cfg3, cfg4) measured the same way in
+           the same run (fewer steps), each with its own parity number.
 Default workload = the configuration the north_star target is quoted on: ER N=1M, avgDeg=32, K=5, G=F=64, B=1, fp32.
 """
 import argparse
@@ -42,11 +50,13 @@ WORKLOADS = {
     # nodes are numbered community by community, so gathers have the locality a real graph ordering would give
     "sbm1m": dict(graph="sbm", N=1_000_000, deg=32, E=1, K=5, G=64, F=64, B=1, seed=6, communities=1000, intra=0.8),
 }
+PARITY_TOL = 1e-4      # north_star tolerance (fp32); fp64 runs are held to 1e-10
 
 
-def describe(w):
-    return "%s N=%d avgDeg=%d E=%d K=%d G=%d F=%d B=%d fp32" % (
-        {"er": "Erdos-Renyi", "knn": "kNN-like", "sbm": "SBM(%d communities)" % w.get("communities", 0)}[w["graph"]], w["N"], w["deg"], w["E"], w["K"], w["G"], w["F"], w["B"])
+def describe(w, dtype="f32"):
+    return "%s N=%d avgDeg=%d E=%d K=%d G=%d F=%d B=%d %s" % (
+        {"er": "Erdos-Renyi", "knn": "kNN-like", "sbm": "SBM(%d communities)" % w.get("communities", 0)}[w["graph"]],
+        w["N"], w["deg"], w["E"], w["K"], w["G"], w["F"], w["B"], "fp64" if dtype == "f64" else "fp32")
 
 
 def make_gso(w):
@@ -75,6 +85,29 @@ def measured_peak_gbs():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def usable_cores():
+    """Host threads this process may really use: CPU affinity mask, capped by the cgroup CPU quota when there is one."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, q // per))
+            break
+        except Exception:
+            continue
+    return max(1, n)
 
 
 class ClockSampler:
@@ -154,23 +187,29 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------
-# CPU baseline / reference arm: dense torch port of the reference algorithm on a bounded sample
+# CPU legs: the reference's dense algorithm on a bounded sample (reference arm / cpu_baseline), a sparse restatement at
+# the full size (labelled "not reference code"), and the fp64 oracle forward used by the parity check
 # ------------------------------------------------------------------------------------------------------
-def cpu_dense_sample(w, n_dense, reps):
-    """Reference algorithm (dense E x N x N GSO, K-1 batched GEMMs + contraction) at N = n_dense with the workload's
-    avgDeg/K/G/F/B.  Returns (ops_per_s, seconds_per_forward, nnz)."""
+def seeded_taps(w, tdt=torch.float32):
+    g = torch.Generator().manual_seed(0)
+    bound = 1.0 / np.sqrt(w["G"] * w["K"])
+    h = ((torch.rand(w["F"], w["E"], w["K"], w["G"], generator=g) * 2 - 1) * bound).to(tdt)
+    b = ((torch.rand(w["F"], 1, generator=g) * 2 - 1) * bound).to(tdt)
+    return h, b
+
+
+def cpu_dense_sample(w, n_dense, reps, threads):
+    """Reference algorithm (dense E x N x N GSO, K-1 batched GEMMs + contraction; graphML.py:152-175) at N = n_dense with
+    the workload's avgDeg/K/G/F/B.  `threads` host threads, one warm-up, median of `reps`.
+    Returns (ops_per_s, seconds_per_forward, nnz, all_times)."""
     import lsigf_oracle as orc
     from gnn_b200 import graphs
-    torch.set_num_threads(os.cpu_count() or 1)
-    ww = dict(w, N=n_dense)
+    torch.set_num_threads(threads)
     gso = graphs.er_gso(n_dense, w["deg"], seed=w["seed"], E=w["E"]) if w["graph"] != "knn" else \
         graphs.knn_like_gso(n_dense, w["deg"], seed=w["seed"])
     S = gso.to_dense().float()
-    g = torch.Generator().manual_seed(0)
-    bound = 1.0 / np.sqrt(w["G"] * w["K"])
-    h = (torch.rand(w["F"], w["E"], w["K"], w["G"], generator=g) * 2 - 1) * bound
-    b = (torch.rand(w["F"], 1, generator=g) * 2 - 1) * bound
-    x = torch.randn(w["B"], w["G"], n_dense, generator=g)
+    h, b = seeded_taps(w)
+    x = torch.randn(w["B"], w["G"], n_dense, generator=torch.Generator().manual_seed(1))
     with torch.no_grad():
         orc.lsigf_dense_torch(h, S, x, b)  # warm-up
         ts = []
@@ -179,22 +218,19 @@ def cpu_dense_sample(w, n_dense, reps):
             orc.lsigf_dense_torch(h, S, x, b)
             ts.append(time.perf_counter() - t0)
     t = float(np.median(ts))
-    ops = ww["E"] * (gso.nnz() / ww["E"]) * (w["K"] - 1) * w["B"] * w["G"]
-    return ops / t, t, gso.nnz()
+    ops = float(gso.nnz()) * (w["K"] - 1) * w["B"] * w["G"]
+    return ops / t, t, gso.nnz(), ts
 
 
-def cpu_sparse_sample(w, gso, reps=2):
+def cpu_sparse_sample(w, gso, threads, reps=3):
     """The same filter at the workload's FULL size with torch.sparse CSR x dense products on the host cores
     (oracle/lsigf_oracle.py:lsigf_sparse_torch).  NOT reference code — the reference has no sparse path; it shows what a
-    CPU could do with the sparse formulation."""
+    CPU could do with the sparse formulation, and it is the one CPU number taken at the same size as the GPU's."""
     import warnings
     import lsigf_oracle as orc
-    torch.set_num_threads(os.cpu_count() or 1)
-    g = torch.Generator().manual_seed(0)
-    bound = 1.0 / np.sqrt(w["G"] * w["K"])
-    h = (torch.rand(w["F"], w["E"], w["K"], w["G"], generator=g) * 2 - 1) * bound
-    b = (torch.rand(w["F"], 1, generator=g) * 2 - 1) * bound
-    x = torch.randn(w["B"], w["G"], w["N"], generator=g)
+    torch.set_num_threads(threads)
+    h, b = seeded_taps(w)
+    x = torch.randn(w["B"], w["G"], w["N"], generator=torch.Generator().manual_seed(1))
     csr = [(r, c, v.astype(np.float32)) for (r, c, v) in gso.csr]
     ts = []
     with torch.no_grad(), warnings.catch_warnings():
@@ -204,10 +240,33 @@ def cpu_sparse_sample(w, gso, reps=2):
             t0 = time.perf_counter()
             orc.lsigf_sparse_torch(h, csr, x, b, prepared=prepared)
             ts.append(time.perf_counter() - t0)
-    t = float(min(ts))
+    t = float(np.median(ts))
     ops = float(gso.nnz()) * (w["K"] - 1) * w["B"] * w["G"]
-    return {"value": ops / t, "unit": "edge-feature-op/s", "cores": os.cpu_count(), "kind": "port-sparse (not reference code)",
-            "sample": "full workload (N=%d, nnz=%d), torch.sparse CSR, best of %d forwards of %.2f s" % (w["N"], gso.nnz(), reps, t)}
+    return {"value": ops / t, "unit": "edge-feature-op/s", "cores": threads, "kind": "port-sparse (not reference code)",
+            "same_size_as_gpu": True,
+            "sample": "full workload (N=%d, nnz=%d), torch.sparse CSR, median of %d forwards of %.2f s" % (w["N"], gso.nnz(), reps, t)}
+
+
+def oracle_forward_nm(gso, h, b, x_nm, B, G):
+    """fp64 oracle forward (oracle/lsigf_oracle.py:lsigf_sparse_stream, sparse products threaded over the host cores) of a
+    node-major x [N, B*G]; returns y node-major [N, B*F] float64."""
+    import scipy.sparse as sp
+    import lsigf_oracle as orc
+    N = gso.N
+    S = [sp.csr_matrix((v.astype(np.float64), c, r), shape=(N, N)) for (r, c, v) in gso.csr]
+    x = x_nm.double().numpy().reshape(N, B, G).transpose(1, 2, 0)                         # [B, G, N]
+    y = orc.lsigf_sparse_stream(h.double().numpy(), S, x, None if b is None else b.double().numpy(), spmm=orc.threaded_spmm)
+    F = h.shape[0]
+    return np.ascontiguousarray(y.transpose(2, 0, 1).reshape(N, B * F))
+
+
+def max_rel(got_nm, want_nm):
+    """max|a - ref| / max|ref| with the comparison done on the GPU when the operands are large."""
+    want = torch.from_numpy(want_nm)
+    if got_nm.is_cuda:
+        want = want.to(got_nm.device)
+    d = (got_nm.double() - want).abs().max().item()
+    return float(d / max(want.abs().max().item(), 1e-300))
 
 
 def pick_dense_n(w):
@@ -217,25 +276,39 @@ def pick_dense_n(w):
     return int(min(w["N"], max(1024, min(n, 16384))))
 
 
+def cpu_baseline_block(w, reps):
+    threads = usable_cores()
+    n_dense = pick_dense_n(w)
+    ops_s, t, nnz_d, ts = cpu_dense_sample(w, n_dense, reps, threads)
+    return ops_s, t, {"value": ops_s, "unit": "edge-feature-op/s", "cores": threads, "kind": "port",
+                      "threads_pinned": threads, "host_cpus_visible": os.cpu_count(),
+                      "sample": "reference dense torch.matmul algorithm at N=%d (nnz=%d), same avgDeg/K/G/F/B; 1 warm-up, "
+                                "median of %d forwards (min %.2f s, median %.2f s, max %.2f s); the dense algorithm is "
+                                "O(N^2) and cannot hold N=%d" % (n_dense, nnz_d, len(ts), min(ts), t, max(ts), w["N"])}
+
+
 def run_reference_arm(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_dense = pick_dense_n(w)
     t_start = time.time()
-    # one "step" = one dense forward on the bounded sample
-    ops_s, t, nnz = cpu_dense_sample(w, n_dense, reps=max(1, args.steps))
+    ops_s, t, block = cpu_baseline_block(w, reps=max(1, min(args.steps, 7)))   # one "step" = one dense forward
     line = {
         "impl": "reference", "metric": "LSIGF edge-feature ops/s", "value": ops_s, "unit": "edge-feature-op/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": describe(w), "note": "CPU dense torch.matmul algorithm of the reference (port)"},
-        "cpu_baseline": {"value": ops_s, "unit": "edge-feature-op/s", "cores": os.cpu_count(), "kind": "port",
-                         "sample": "dense GSO at N=%d (nnz=%d), same avgDeg/K/G/F/B as the workload; the dense "
-                                   "algorithm is O(N^2) and cannot hold N=%d" % (n_dense, nnz, w["N"])},
+        "config": {"workload": describe(w), "note": "CPU dense torch.matmul algorithm of the reference (port; the "
+                   "reference package cannot be pip-installed offline: poetry-core build backend missing)"},
+        "cpu_baseline": block,
         "e2e": {"value": ops_s, "unit": "edge-feature-op/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "wall_s": time.time() - t_start,
+        "gpu_launches": 0,
     }
+    if not args.no_full_size_cpu and w["B"] * w["G"] <= 256:
+        try:   # the one CPU figure at the GPU arm's own size (sparse restatement, labelled as such)
+            line["cpu_sparse_full_size"] = cpu_sparse_sample(w, make_gso(w), usable_cores())
+        except Exception as exc:
+            line["cpu_sparse_full_size"] = {"error": str(exc)[:200]}
+    line["wall_s"] = time.time() - t_start
     print(json.dumps(line))
 
 
@@ -288,72 +361,133 @@ class _JsonOnlyStdout:
         os.write(self._real, (text + "\n").encode())
 
 
-def run_gpu_arm(args, w):
-    import torch.distributed as dist
-    import gnn_b200
-    from gnn_b200 import _cabi
-    out_fd = _JsonOnlyStdout()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the GPU arm has no CPU fallback)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("B200GF_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=dev)
-    lib = _cabi.load()
-    E, K, G, F, B, N = w["E"], w["K"], w["G"], w["F"], w["B"], w["N"]
-    tdt = torch.float64 if args.dtype == "f64" else torch.float32      # the reference's examples run in float64
-    es = 8 if args.dtype == "f64" else 4
-    gso = make_gso(w).astype(tdt)
-    nnz_e = gso.nnz() // E
-    ops_per_step = float(gso.nnz()) * (K - 1) * B * G
-    g = torch.Generator().manual_seed(0)
-    bound = 1.0 / np.sqrt(G * K)
-    h = ((torch.rand(F, E, K, G, generator=g) * 2 - 1) * bound).to(dev, tdt)
-    b = ((torch.rand(F, 1, generator=g) * 2 - 1) * bound).to(dev, tdt)
-    peak, peak_src = measured_peak_gbs()
-    out = {}
+class Ctx:
+    """Per-process measurement context (device, ranks, library handle, timing helper)."""
 
-    def timed(fn, steps, warmup):
+    def __init__(self, args):
+        import torch.distributed as dist
+        from gnn_b200 import _cabi
+        self.args, self.dist = args, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (the GPU arm has no CPU fallback)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ["NCCL_DEBUG"] = os.environ.get("B200GF_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.lib = _cabi.load()
+        self.tdt = torch.float64 if args.dtype == "f64" else torch.float32
+        self.es = 8 if args.dtype == "f64" else 4
+        self.tol = 1e-10 if args.dtype == "f64" else PARITY_TOL
+        self.peak, self.peak_src = measured_peak_gbs()
+
+    def timed(self, fn, steps, warmup):
+        """W warm-up calls, barrier + synchronize, exactly `steps` calls between two CUDA events, synchronize + barrier;
+        max over ranks.  Returns (ms per step, library kernel launches inside the timed region on this rank)."""
         for _ in range(warmup):
             fn()
-        if world > 1:
-            dist.barrier()
+        if self.world > 1:
+            self.dist.barrier()
         torch.cuda.synchronize()
+        self.lib.b200gf_launch_count(1)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
         torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.barrier()
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()) / steps
+        launches = int(self.lib.b200gf_launch_count(1))
+        ms = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        return float(ms.item()) / steps, launches
 
-    if world == 1:
-        x = torch.randn(B, G, N, generator=g).to(dev, tdt)      # reference layout, resident in HBM
-        plan = gso.plan(dev)
-        fwd = lambda: gnn_b200.LSIGF(h, gso, x, b)              # noqa: E731  (layout conversion inside the step)
-        hops = E * (K - 1)
-        cap = hops * (args.steps + args.warmup)
-        lib.b200gf_profile_hops(plan.handle, cap)
-        with torch.no_grad(), ClockSampler(local) as clk:
-            ms = timed(fwd, args.steps, args.warmup)
-        hop_ms = ctypes_floats(lib, plan, cap)[hops * args.warmup:]   # launches inside the timed region only
-        lib.b200gf_profile_hops(plan.handle, 0)
-        launches_per_step = 1 + 1 + E * (K - 1) + 1             # to_node_major, pack_taps, hops, tap_contract
+
+def ctypes_floats(lib, plan, n):
+    import ctypes
+    buf = (ctypes.c_float * n)()
+    got = lib.b200gf_profile_read(plan.handle, buf, n)
+    return [float(buf[i]) for i in range(max(0, got))]
+
+
+def load_ncu_traffic(workload, dtype):
+    """DRAM bytes per hop launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full`
+    capture of this workload / dtype / kernel version (profiles/ncu_traffic.json names the capture file), or null."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        d = json.load(open(p))
+        return d.get("%s:%s" % (workload, dtype), d.get(workload) if dtype == "f32" else None)
+    except Exception:
+        return None
+
+
+def hop_roofline(ctx, hop_ms, step_ms_total, nnz, rows, C, kernel, workload=None):
+    if not hop_ms:
+        return None
+    hop_bytes = hop_algorithmic_bytes(nnz, rows, C, ctx.es)
+    avg = float(np.mean(hop_ms))
+    achieved = hop_bytes / (avg * 1e-3) / 1e9
+    traffic = load_ncu_traffic(workload, ctx.args.dtype) if workload else None
+    out = {"bound": "hbm", "achieved": achieved, "peak": ctx.peak, "unit": "GB/s", "frac": achieved / ctx.peak,
+           "traffic": traffic, "kernel": kernel, "bytes_per_launch": hop_bytes, "ms_per_launch": avg,
+           "launches_timed": len(hop_ms), "peak_source": ctx.peak_src,
+           "kernel_share_of_step": float(np.sum(hop_ms)) / step_ms_total}
+    if traffic:
+        out["dram_frac"] = traffic / (avg * 1e-3) / 1e9 / ctx.peak      # actual DRAM bytes / time / copy peak
+    return out
+
+
+def single_gpu_workload(ctx, name, w, steps, warmup, full):
+    """One workload on one GPU: timed forward (+ hop profile, parity; with `full` also e2e and forward+backward)."""
+    import gnn_b200
+    args, dev, tdt, es, lib = ctx.args, ctx.dev, ctx.tdt, ctx.es, ctx.lib
+    E, K, G, F, B, N = w["E"], w["K"], w["G"], w["F"], w["B"], w["N"]
+    gso = make_gso(w).astype(tdt)
+    nnz_e = gso.nnz() // E
+    ops_per_step = float(gso.nnz()) * (K - 1) * B * G
+    h_cpu, b_cpu = seeded_taps(w, tdt)
+    h, b = h_cpu.to(dev), b_cpu.to(dev)
+    g = torch.Generator().manual_seed(1)
+    x_cpu = torch.randn(B, G, N, generator=g).to(tdt)
+    x = x_cpu.to(dev)                                         # reference layout, resident in HBM
+    plan = gso.plan(dev)
+    fwd = lambda: gnn_b200.LSIGF(h, gso, x, b)               # noqa: E731  (layout conversion inside the step)
+    hops = E * (K - 1)
+    cap = hops * (steps + warmup)
+    lib.b200gf_profile_hops(plan.handle, cap)
+    with torch.no_grad(), ClockSampler(ctx.local) as clk:
+        ms, launches = ctx.timed(fwd, steps, warmup)
+    hop_ms = ctypes_floats(lib, plan, cap)[hops * warmup:]   # launches inside the timed region only
+    lib.b200gf_profile_hops(plan.handle, 0)
+    out = {"ms_per_step": ms, "value": ops_per_step / (ms * 1e-3), "unit": "edge-feature-op/s", "nnz": gso.nnz(),
+           "ops_per_step": ops_per_step, "gpu_launches": launches, "clocks": clk.summary(),
+           "roofline": hop_roofline(ctx, hop_ms, ms * steps, nnz_e, N, B * G, "spmm_hop_v2_kernel" if B * G * es > 128
+                                    else "spmm_hop_multirow_kernel", workload=name)}
+    if not args.no_check:
+        t0 = time.time()
+        with torch.no_grad():
+            y = fwd()                                        # [B, F, N] view of the node-major result
+            y_nm = y.permute(2, 0, 1).reshape(N, B * F)
+        x_nm = x_cpu.permute(2, 0, 1).reshape(N, B * G)
+        want = oracle_forward_nm(gso, h_cpu, b_cpu, x_nm, B, G)
+        out["parity_max_rel"] = max_rel(y_nm, want)
+        out["parity_note"] = "all %d x %d outputs vs the fp64 CPU oracle at full size (%.1f s on the host)" % (N, B * F, time.time() - t0)
+        del y, y_nm, want
+    if full:
         # end-to-end through the public API with pinned host buffers
-        xh = torch.randn(B, G, N, generator=g).to(tdt).pin_memory()
+        xh = x_cpu.pin_memory()
         pipe = E2EPipeline(dev, xh, (B, F, N), lambda xd: gnn_b200.to_feature_major(gnn_b200.LSIGF(h, gso, xd, b)))
         yh = pipe.yh[0]
         with torch.no_grad():
-            ms_e2e = timed(pipe.step, args.steps, 3)
+            ms_e2e, _ = ctx.timed(pipe.step, steps, 3)
+        out["e2e"] = {"value": ops_per_step / (ms_e2e * 1e-3), "unit": "edge-feature-op/s",
+                      "h2d_bytes_per_step": xh.numel() * es, "d2h_bytes_per_step": yh.numel() * es, "ms_per_step": ms_e2e}
+        del pipe
         # forward + backward (reported beside the headline; SURVEY.md §8d asks for both)
         xg = x.clone().requires_grad_(True)
         hg = h.clone().requires_grad_(True)
@@ -364,133 +498,308 @@ def run_gpu_arm(args, w):
             xg.grad = hg.grad = bg.grad = None
             gnn_b200.LSIGF(hg, gso, xg, bg).backward(dy)
 
-        ms_fb = timed(fwd_bwd, max(3, args.steps // 2), 2)
+        ms_fb, _ = ctx.timed(fwd_bwd, max(3, steps // 2), 2)
         out["fwd_bwd"] = {"ms_per_step": ms_fb, "unit": "edge-feature-op/s",
                           "value": float(gso.nnz()) * (K - 1) * B * (G + F) / (ms_fb * 1e-3),
                           "note": "forward hops on B*G columns + backward hops on B*F columns per step"}
-        C = B * G
-        hop_bytes = hop_algorithmic_bytes(nnz_e, N, C, es)
-        hop_avg_ms = float(np.mean(hop_ms)) if len(hop_ms) else float("nan")
-        achieved = hop_bytes / (hop_avg_ms * 1e-3) / 1e9
-        out["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                           "traffic": load_ncu_traffic(args.workload), "kernel": "spmm_hop_kernel",
-                           "bytes_per_launch": hop_bytes, "ms_per_launch": hop_avg_ms, "launches_timed": len(hop_ms),
-                           "peak_source": peak_src, "kernel_share_of_step": float(np.sum(hop_ms)) / (ms * args.steps)}
-        out["e2e"] = {"value": ops_per_step / (ms_e2e * 1e-3), "unit": "edge-feature-op/s",
-                      "h2d_bytes_per_step": xh.numel() * es, "d2h_bytes_per_step": yh.numel() * es, "ms_per_step": ms_e2e}
-        out["clocks"] = clk.summary()
-        parallelism = "single"
-    else:
-        from gnn_b200.distributed import PartitionedLSIGF
-        part = PartitionedLSIGF(gso, mode=args.mode, device=dev, fused=False if args.no_fused else None, fence=args.fence)
-        if args.mode == "nodes":
-            x_local = torch.randn(part.rows_per_rank, B * G, generator=torch.Generator().manual_seed(rank)).to(dev, tdt)
+    out["l2"] = ("inputs larger than L2 (x and every z_k are %d MB each; no flush needed)" % (N * B * G * es // 2 ** 20)
+                 if N * B * G * es > 126 * 2 ** 20 else "working set fits L2: numbers are L2-warm")
+    return out, gso
+
+
+def multi_gpu_selftest(ctx):
+    """Forward AND backward of both shardings on a small graph against the fp64 oracle, over the same NCCL / NVLink ranks
+    the bench uses (the partitioned backward and the fused kernels above 2 ranks had no hardware evidence)."""
+    import scipy.sparse as sp
+    import lsigf_oracle as orc
+    from gnn_b200 import graphs
+    from gnn_b200.distributed import PartitionedLSIGF
+    dist, dev, world, rank = ctx.dist, ctx.dev, ctx.world, ctx.rank
+    N, E, K, B = 20011, 2, 4, 2                                   # N not divisible by the world size: padded last block
+    G = F = 64
+    res = {}
+    for dtype, tol in ((torch.float32, 1e-4), (torch.float64, 1e-10)):
+        gso = graphs.er_gso(N, 12, seed=77, E=E).astype(dtype)
+        gen = torch.Generator().manual_seed(5)
+        h = (torch.rand(F, E, K, G, generator=gen, dtype=torch.float64) - 0.5).to(dtype)
+        b = (torch.rand(F, 1, generator=gen, dtype=torch.float64) - 0.5).to(dtype)
+        x_nm = torch.randn(N, B * G, generator=gen, dtype=torch.float64).to(dtype)
+        dy_nm = torch.randn(N, B * F, generator=gen, dtype=torch.float64).to(dtype)
+        want = None
+        if rank == 0:
+            S = [sp.csr_matrix((v.astype(np.float64), c, r), shape=(N, N)) for (r, c, v) in gso.csr]
+            x = x_nm.double().numpy().reshape(N, B, G).transpose(1, 2, 0)
+            dy = dy_nm.double().numpy().reshape(N, B, F).transpose(1, 2, 0)
+            y_ref = orc.lsigf_sparse_stream(h.double().numpy(), S, x, b.double().numpy())
+            dh_ref, dx_ref, db_ref = orc.lsigf_grads_sparse_stream(h.double().numpy(), S, x, dy, (F, 1))
+            want = dict(y=y_ref.transpose(2, 0, 1).reshape(N, B * F), dh=dh_ref, dx=dx_ref.transpose(2, 0, 1).reshape(N, B * G), db=db_ref)
+        for mode in ("nodes", "features"):
+            part = PartitionedLSIGF(gso, mode=mode, device=dev)
+            R = part.rows_per_rank
+            pad = lambda t: torch.cat((t, torch.zeros(part.n_pad - N, t.shape[1], dtype=t.dtype)))   # noqa: E731
+            if mode == "nodes":
+                x_local = pad(x_nm)[part.r0:part.r1].to(dev)
+            else:
+                g0, g1 = part.feature_slice(G)
+                x_local = x_nm.view(N, B, G)[:, :, g0:g1].reshape(N, B * (g1 - g0)).contiguous().to(dev)
+            dy_rows = pad(dy_nm)[part.r0:part.r1].to(dev)
+            hd, bd = h.to(dev), b.to(dev)
+            with torch.no_grad():
+                for _ in range(2):                               # twice: symmetric buffers are reused across calls
+                    y_rows = part.forward(hd, x_local, bd, B=B)
+                dh, dx, db = part.backward(hd, x_local, dy_rows, B=B, want_db=True)
+            ys = [torch.empty((R, B * F), dtype=dtype, device=dev) for _ in range(world)]
+            dist.all_gather(ys, y_rows.contiguous())
+            if mode == "nodes":
+                dxs = [torch.empty((R, B * G), dtype=dtype, device=dev) for _ in range(world)]
+                dist.all_gather(dxs, dx.contiguous())
+                dx_full = torch.cat(dxs)[:N]
+            else:
+                per = (G + world - 1) // world
+                mine = torch.zeros(N, B, per, dtype=dtype, device=dev)
+                g0, g1 = part.feature_slice(G)
+                mine[:, :, :g1 - g0] = dx.reshape(N, B, g1 - g0)
+                dxs = [torch.empty_like(mine) for _ in range(world)]
+                dist.all_gather(dxs, mine)
+                dx_full = torch.cat([d[:, :, :max(0, min(G, (p + 1) * per) - min(G, p * per))] for p, d in enumerate(dxs)], dim=2).reshape(N, B * G)
+            if rank == 0:
+                key = "%s_%s" % (mode, "f32" if dtype == torch.float32 else "f64")
+                errs = {"y": max_rel(torch.cat(ys)[:N], want["y"]), "dh": max_rel(dh, want["dh"]),
+                        "dx": max_rel(dx_full, want["dx"]), "db": max_rel(db, want["db"]), "tol": tol,
+                        "fused": bool(part.fused)}
+                if mode == "nodes" and part._arenas:
+                    errs["symmetric_memory"] = next(iter(part._arenas.values())).kind
+                errs["ok"] = bool(max(errs[k] for k in ("y", "dh", "dx", "db")) < tol)
+                res[key] = errs
+            del part
+    return res
+
+
+def multi_gpu_arm(ctx, w, out_fd):
+    from gnn_b200.distributed import PartitionedLSIGF
+    args, dev, tdt, es, lib, dist = ctx.args, ctx.dev, ctx.tdt, ctx.es, ctx.lib, ctx.dist
+    world, rank = ctx.world, ctx.rank
+    E, K, G, F, B, N = w["E"], w["K"], w["G"], w["F"], w["B"], w["N"]
+    gso = make_gso(w).astype(tdt)
+    nnz_e = gso.nnz() // E
+    ops_per_step = float(gso.nnz()) * (K - 1) * B * G
+    h_cpu, b_cpu = seeded_taps(w, tdt)
+    h, b = h_cpu.to(dev), b_cpu.to(dev)
+    x_nm = torch.randn(N, B * G, generator=torch.Generator().manual_seed(1)).to(tdt)     # same full x on every rank
+    out = {}
+
+    def build(mode):
+        part = PartitionedLSIGF(gso, mode=mode, device=dev, fused=False if args.no_fused else None, fence=args.fence,
+                                symm_backend=args.symm)
+        if mode == "nodes":
+            xp = torch.cat((x_nm, torch.zeros(part.n_pad - N, B * G, dtype=tdt)))
+            x_local = xp[part.r0:part.r1].contiguous().to(dev)
         else:
             g0, g1 = part.feature_slice(G)
-            x_local = torch.randn(N, B * (g1 - g0), generator=torch.Generator().manual_seed(rank)).to(dev, tdt)
+            x_local = x_nm.view(N, B, G)[:, :, g0:g1].reshape(N, B * (g1 - g0)).contiguous().to(dev)
         fwd = lambda: part.forward(h, x_local, b, B=B)          # noqa: E731
-        use_graph = args.graph and part.fused and args.fence == "flags" and args.mode == "features"
-        if use_graph:
-            with torch.no_grad():
-                fwd = part.graphed(h, x_local, b, B=B)
-        hops = E * (K - 1)
-        cap = hops * (args.steps + args.warmup)
+        graphed = False
+        if (not args.no_graph) and part.fused and args.fence == "flags":
+            try:
+                with torch.no_grad():
+                    fwd = part.graphed(h, x_local, b, B=B)
+                graphed = True
+            except Exception as exc:                             # keep the eager step; say why
+                out.setdefault("graph_errors", {})[mode] = repr(exc)[:200]
+        return part, x_local, fwd, graphed
+
+    modes = ["nodes", "features"] if args.mode == "auto" else [args.mode]
+    tried = {}
+    built = {}
+    for mode in modes:
+        built[mode] = build(mode)
+        with torch.no_grad():
+            ms_probe, _ = ctx.timed(built[mode][2], 5, 3)
+        tried[mode] = ms_probe
+    mode = min(tried, key=tried.get)
+    if len(modes) > 1:
+        pick = torch.tensor([modes.index(mode)], device=dev)
+        dist.broadcast(pick, 0)                                  # every rank times the same sharding
+        mode = modes[int(pick.item())]
+    for m in modes:
+        if m != mode:
+            built.pop(m)
+            torch.cuda.empty_cache()
+    part, x_local, fwd, graphed = built[mode]
+    hops = E * (K - 1)
+    cap = hops * (args.steps + args.warmup)
+    if not graphed:
         lib.b200gf_profile_hops(part.plan.handle, cap)
-        with torch.no_grad(), ClockSampler(local) as clk:
-            ms = timed(fwd, args.steps, args.warmup)
+    with torch.no_grad(), ClockSampler(ctx.local) as clk:
+        ms, launches = ctx.timed(fwd, args.steps, args.warmup)
+    hop_ms = []
+    if not graphed:
         hop_ms = ctypes_floats(lib, part.plan, cap)[hops * args.warmup:]
         lib.b200gf_profile_hops(part.plan.handle, 0)
-        # e2e: every rank copies its shard in from pinned host memory and its result rows back
-        xh = x_local.cpu().pin_memory()
-        if use_graph:
-            def compute(xd):
-                x_local.copy_(xd)
-                return fwd().contiguous()
-        else:
-            compute = lambda xd: part.forward(h, xd, b, B=B).contiguous()   # noqa: E731
-        pipe = E2EPipeline(dev, xh, (part.rows_per_rank, B * F), compute)
-        yh = pipe.yh[0]
+    else:
+        # a replayed graph launches no kernel from the host: count the graph's kernels once by running one eager step,
+        # and time the hops in a separate eager pass (same kernels, same buffers)
         with torch.no_grad():
-            ms_e2e = timed(pipe.step, args.steps, 3)
-        if args.bwd:   # opt-in: forward + the collective backward (dh, db all-reduced; dx sharded like x)
-            dy_rows = torch.randn(part.rows_per_rank, B * F, generator=torch.Generator().manual_seed(100 + rank)).to(dev, tdt)
-
-            def fwd_bwd():
+            lib.b200gf_launch_count(1)
+            part.forward(h, x_local, b, B=B)
+            launches = int(lib.b200gf_launch_count(1)) * args.steps
+            lib.b200gf_profile_hops(part.plan.handle, hops * 8)
+            for _ in range(8):
                 part.forward(h, x_local, b, B=B)
-                part.backward(h, x_local, dy_rows, B=B, want_db=True)
+            torch.cuda.synchronize()
+            hop_ms = ctypes_floats(lib, part.plan, hops * 8)[hops * 3:]
+            lib.b200gf_profile_hops(part.plan.handle, 0)
+    # parity of the timed path at full size: gather every rank's rows, compare with the CPU oracle on rank 0
+    if not args.no_check:
+        with torch.no_grad():
+            y_rows = fwd().contiguous()
+        ys = [torch.empty_like(y_rows) for _ in range(world)]
+        dist.all_gather(ys, y_rows)
+        if rank == 0:
+            t0 = time.time()
+            want = oracle_forward_nm(gso, h_cpu, b_cpu, x_nm, B, G)
+            out["parity_max_rel"] = max_rel(torch.cat(ys)[:N], want)
+            out["parity_note"] = "all %d x %d outputs (rows gathered from %d ranks) vs the fp64 CPU oracle at full size (%.1f s on the host)" % (N, B * F, world, time.time() - t0)
+            del want
+        del ys
+        dist.barrier()
+    # e2e: every rank copies its shard in from pinned host memory and its result rows back
+    xh = x_local.cpu().pin_memory()
+    if graphed:
+        def compute(xd):
+            x_local.copy_(xd)
+            return fwd().contiguous()
+    else:
+        compute = lambda xd: part.forward(h, xd, b, B=B).contiguous()   # noqa: E731
+    pipe = E2EPipeline(dev, xh, (part.rows_per_rank, B * F), compute)
+    yh = pipe.yh[0]
+    with torch.no_grad():
+        ms_e2e, _ = ctx.timed(pipe.step, args.steps, 3)
+    del pipe
+    if not args.no_bwd:   # forward + the collective backward (dh, db all-reduced; dx sharded like x)
+        dy_rows = torch.randn(part.rows_per_rank, B * F, generator=torch.Generator().manual_seed(100 + rank)).to(dev, tdt)
 
-            with torch.no_grad():
-                ms_fb = timed(fwd_bwd, max(3, args.steps // 2), 2)
-            out["fwd_bwd"] = {"ms_per_step": ms_fb, "unit": "edge-feature-op/s",
-                              "value": float(gso.nnz()) * (K - 1) * B * (G + F) / (ms_fb * 1e-3),
-                              "note": "partitioned forward + backward (NCCL exchanges in the backward)"}
-        # my kernels per rank and step: pack_taps, split_w, tc_contract, the hops, and the scatter of the k = 0 slice
-        launches_per_step = (E * (K - 1) + 3 + (1 if part.fused else 0)) * world
-        if args.mode == "nodes":
-            c_loc, nnz_loc, rows_loc = B * G, part.local_nnz // E, part.rows_per_rank
-        else:
-            g0, g1 = part.feature_slice(G)
-            c_loc, nnz_loc, rows_loc = B * (g1 - g0), nnz_e, N
-        hop_bytes = hop_algorithmic_bytes(nnz_loc, rows_loc, c_loc, es)
-        hop_avg_ms = float(np.mean(hop_ms)) if len(hop_ms) else float("nan")
-        achieved = hop_bytes / (hop_avg_ms * 1e-3) / 1e9
-        out["roofline"] = None if not hop_ms else {
-                           "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                           "traffic": None, "kernel": "spmm_hop_kernel (rank 0 shard: %d rows x %d columns, %d nnz)" %
-                                                        (rows_loc, c_loc, nnz_loc),
-                           "bytes_per_launch": hop_bytes, "ms_per_launch": hop_avg_ms, "launches_timed": len(hop_ms),
-                           "peak_source": peak_src, "kernel_share_of_step": float(np.sum(hop_ms)) / (ms * args.steps)}
-        out["e2e"] = {"value": ops_per_step / (ms_e2e * 1e-3), "unit": "edge-feature-op/s",
-                      "h2d_bytes_per_step": xh.numel() * es * world, "d2h_bytes_per_step": yh.numel() * es * world,
-                      "ms_per_step": ms_e2e}
-        out["clocks"] = clk.summary()
-        parallelism = "%s-partition x%d%s%s" % (args.mode, world,
-                                                " (fused hop+NVLink scatter, %s fence)" % args.fence if part.fused else "",
-                                                ", CUDA graph" if use_graph else "")
+        def fwd_bwd():
+            part.forward(h, x_local, b, B=B)
+            part.backward(h, x_local, dy_rows, B=B, want_db=True)
 
+        with torch.no_grad():
+            ms_fb, _ = ctx.timed(fwd_bwd, max(3, args.steps // 2), 2)
+        out["fwd_bwd"] = {"ms_per_step": ms_fb, "unit": "edge-feature-op/s",
+                          "value": float(gso.nnz()) * (K - 1) * B * (G + F) / (ms_fb * 1e-3),
+                          "note": "partitioned forward + backward, %s sharding" % mode}
+    if mode == "nodes":
+        c_loc, nnz_loc, rows_loc = B * G, part.local_nnz // E, part.rows_per_rank
+    else:
+        g0, g1 = part.feature_slice(G)
+        c_loc, nnz_loc, rows_loc = B * (g1 - g0), nnz_e, N
+    rf = hop_roofline(ctx, hop_ms, ms * max(1, len(hop_ms) // max(hops, 1)), nnz_loc, rows_loc, c_loc,
+                      "hop kernel, rank 0 shard: %d rows x %d columns, %d nnz%s" %
+                      (rows_loc, c_loc, nnz_loc, " (fused all-gather epilogue)" if mode == "nodes" and part.fused else ""))
+    out["roofline"] = rf
+    out["e2e"] = {"value": ops_per_step / (ms_e2e * 1e-3), "unit": "edge-feature-op/s",
+                  "h2d_bytes_per_step": xh.numel() * es * world, "d2h_bytes_per_step": yh.numel() * es * world,
+                  "ms_per_step": ms_e2e}
+    out["clocks"] = clk.summary()
+    out["modes_probed_ms"] = tried
+    symm = None
+    if mode == "nodes" and part._arenas:
+        symm = next(iter(part._arenas.values())).kind
+    parallelism = "%s-partition x%d%s%s%s" % (
+        mode, world,
+        (" (all-gather fused into the hop kernel: %s, peer-flag fences)" % symm) if (mode == "nodes" and part.fused) else
+        (" (fused hop+NVLink scatter, %s fence)" % args.fence if part.fused else " (NCCL collectives)"),
+        ", CUDA graph" if graphed else "", "")
+    if not args.no_selftest:
+        st = multi_gpu_selftest(ctx)
+        if rank == 0:
+            out["selftest"] = st
+    lt = torch.tensor([launches], device=dev)
+    dist.all_reduce(lt)                                           # launches of all ranks inside the timed region
     if rank == 0:
         line = {
             "metric": "LSIGF edge-feature ops/s", "value": ops_per_step / (ms * 1e-3), "unit": "edge-feature-op/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": describe(w).replace("fp32", "fp64" if args.dtype == "f64" else "fp32"), "name": args.workload, "nnz": gso.nnz(), "parallelism": parallelism,
-                       "l2": "inputs larger than L2 (x and every z_k are %d MB each; no flush needed)" %
-                             (N * B * G * es // 2 ** 20) if N * B * G * es > 126 * 2 ** 20 else
-                             "working set fits L2: numbers are L2-warm",
-                       "ops_per_step": ops_per_step},
-            "gpu_launches": launches_per_step * args.steps,
+            "config": {"workload": describe(w, args.dtype), "name": args.workload, "nnz": gso.nnz(), "parallelism": parallelism,
+                       "l2": "inputs larger than L2 (x and every z_k are %d MB each; no flush needed)" % (N * B * G * es // 2 ** 20)
+                       if N * B * G * es > 126 * 2 ** 20 else "working set fits L2: numbers are L2-warm",
+                       "ops_per_step": ops_per_step,
+                       "note": "x is the node-major shard each rank owns (layout conversion is not part of the N > 1 step)"},
+            "gpu_launches": int(lt.item()),
         }
         line.update(out)
-        if world == 1 and not args.no_cpu_baseline:
-            n_dense = pick_dense_n(w)
-            ops_s, t, nnz_d = cpu_dense_sample(w, n_dense, reps=3)
-            line["cpu_baseline"] = {"value": ops_s, "unit": "edge-feature-op/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": "reference dense torch.matmul algorithm at N=%d (nnz=%d), 3 forwards of "
-                                              "%.2f s; same avgDeg/K/G/F/B" % (n_dense, nnz_d, t)}
-            if w["B"] * w["G"] <= 256:   # second CPU line at the FULL graph size: sparse torch restatement, not reference code
-                try:
-                    line["cpu_sparse_baseline"] = cpu_sparse_sample(w, gso)
-                except Exception as exc:  # never let the extra baseline break the bench line
-                    line["cpu_sparse_baseline"] = {"error": str(exc)[:200]}
+        bad = []
+        if "parity_max_rel" in line and not line["parity_max_rel"] < ctx.tol:
+            bad.append("parity_max_rel %.3e" % line["parity_max_rel"])
+        for k, v in line.get("selftest", {}).items():
+            if not v.get("ok", False):
+                bad.append("selftest %s" % k)
+        line["parity_ok"] = not bad
         out_fd.emit(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+        if bad:
+            sys.stderr.write("bench.py: PARITY FAILURE: %s\n" % ", ".join(bad))
+    dist.barrier()
+    code = 0
+    flag = torch.tensor([1 if (rank == 0 and not line["parity_ok"]) else 0], device=dev)
+    dist.all_reduce(flag)
+    if int(flag.item()):
+        code = 3
+    dist.destroy_process_group()
+    if code:
+        sys.exit(code)
 
 
-def ctypes_floats(lib, plan, n):
-    import ctypes
-    buf = (ctypes.c_float * n)()
-    got = lib.b200gf_profile_read(plan.handle, buf, n)
-    return [float(buf[i]) for i in range(max(0, got))]
-
-
-def load_ncu_traffic(workload):
-    """dram bytes per hop launch from the committed ncu capture of this workload (profiles/), or null."""
-    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    try:
-        return json.load(open(p)).get(workload)
-    except Exception:
-        return None
+def run_gpu_arm(args, w):
+    out_fd = _JsonOnlyStdout()
+    ctx = Ctx(args)
+    if ctx.world > 1:
+        return multi_gpu_arm(ctx, w, out_fd)
+    res, gso = single_gpu_workload(ctx, args.workload, w, args.steps, args.warmup, full=True)
+    line = {
+        "metric": "LSIGF edge-feature ops/s", "value": res["value"], "unit": "edge-feature-op/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": describe(w, args.dtype), "name": args.workload, "nnz": res["nnz"], "parallelism": "single",
+                   "l2": res["l2"], "ops_per_step": res["ops_per_step"]},
+    }
+    for k in ("gpu_launches", "roofline", "e2e", "fwd_bwd", "clocks", "parity_max_rel", "parity_note"):
+        if k in res:
+            line[k] = res[k]
+    bad = []
+    if "parity_max_rel" in res and not res["parity_max_rel"] < ctx.tol:
+        bad.append("%s parity_max_rel %.3e" % (args.workload, res["parity_max_rel"]))
+    # the other single-GPU configurations of BASELINE.json, same run, fewer steps
+    extra = [c for c in args.configs.split(",") if c and c != args.workload] if args.configs else []
+    if extra:
+        line["configs"] = {}
+    for name in extra:
+        torch.cuda.empty_cache()
+        try:
+            r, _ = single_gpu_workload(ctx, name, WORKLOADS[name], max(3, min(args.steps, 10)), 3, full=False)
+            rf = r.get("roofline") or {}
+            line["configs"][name] = {"workload": describe(WORKLOADS[name], args.dtype), "ms_per_step": r["ms_per_step"],
+                                     "value": r["value"], "unit": r["unit"], "parity_max_rel": r.get("parity_max_rel"),
+                                     "hop_frac_of_hbm_peak": rf.get("frac"), "hop_ms": rf.get("ms_per_launch"),
+                                     "hop_share": rf.get("kernel_share_of_step"), "gpu_launches": r["gpu_launches"],
+                                     "l2": r["l2"], "clocks": r["clocks"]}
+            if r.get("parity_max_rel") is not None and not r["parity_max_rel"] < ctx.tol:
+                bad.append("%s parity_max_rel %.3e" % (name, r["parity_max_rel"]))
+        except Exception as exc:   # an extra config must not take the headline line down with it
+            line["configs"][name] = {"error": repr(exc)[:300]}
+    if not args.no_cpu_baseline:
+        _, _, block = cpu_baseline_block(w, reps=5)
+        line["cpu_baseline"] = block
+        if w["B"] * w["G"] <= 256:   # second CPU line at the FULL graph size: sparse torch restatement, not reference code
+            try:
+                line["cpu_sparse_baseline"] = cpu_sparse_sample(w, gso, usable_cores())
+            except Exception as exc:  # never let the extra baseline break the bench line
+                line["cpu_sparse_baseline"] = {"error": str(exc)[:200]}
+    line["parity_ok"] = not bad
+    out_fd.emit(json.dumps(line))
+    if bad:
+        sys.stderr.write("bench.py: PARITY FAILURE: %s\n" % ", ".join(bad))
+        sys.exit(3)
 
 
 def main():
@@ -500,15 +809,23 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="er1m", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="features", choices=["nodes", "features"],
-                    help="multi-GPU sharding (DESIGN.md §4): feature columns (default) or node rows")
+    ap.add_argument("--mode", default="auto", choices=["auto", "nodes", "features"],
+                    help="multi-GPU sharding (DESIGN.md §4): node rows (north_star), feature columns, or probe both and "
+                         "time the faster one (default)")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"], help="arithmetic type (headline: f32)")
+    ap.add_argument("--configs", default="cfg2,cfg3,cfg4",
+                    help="N = 1: other BASELINE.json configurations measured in the same run ('' = none)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-size-cpu", action="store_true", help="reference arm: skip the full-size sparse CPU figure")
+    ap.add_argument("--no-check", action="store_true", help="skip the full-size parity check against the CPU oracle")
+    ap.add_argument("--no-selftest", action="store_true", help="multi-GPU: skip the small forward+backward self-test")
+    ap.add_argument("--no-bwd", action="store_true", help="multi-GPU: skip the forward + partitioned backward timing")
     ap.add_argument("--fence", default="flags", choices=["flags", "nccl"],
                     help="multi-GPU fused path: peer flags in symmetric memory (default) or a 4-byte NCCL all-reduce")
-    ap.add_argument("--graph", action="store_true", help="multi-GPU fused path: replay the step as a CUDA graph")
-    ap.add_argument("--no-fused", action="store_true", help="multi-GPU: NCCL all-to-all instead of the fused NVLink scatter")
-    ap.add_argument("--bwd", action="store_true", help="multi-GPU: also time forward + partitioned backward (fwd_bwd key)")
+    ap.add_argument("--no-graph", action="store_true", help="multi-GPU fused path: do not replay the step as a CUDA graph")
+    ap.add_argument("--no-fused", action="store_true", help="multi-GPU: NCCL collectives instead of the fused kernels")
+    ap.add_argument("--symm", default="auto", choices=["auto", "torch", "ipc"],
+                    help="node sharding: symmetric memory through torch (multicast when available) or plain CUDA IPC")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     w = WORKLOADS[args.workload]

@@ -23,6 +23,7 @@ PP = ctypes.POINTER(ctypes.c_void_p)
 _SIGNATURES = {
     "b200gf_strerror": (ctypes.c_char_p, [c_int]),
     "b200gf_version": (c_int, []),
+    "b200gf_launch_count": (c_i64, [c_int]),
     "b200gf_plan_create": (c_int, [PP, c_int, c_i64, c_int, PP, PP, PP, c_int]),
     "b200gf_plan_create_ops": (c_int, [PP, c_int, c_i64, c_i64, c_int, PP, PP, PP, PP, PP, PP, c_int]),
     "b200gf_plan_destroy": (None, [c_vp]),
@@ -38,6 +39,8 @@ _SIGNATURES = {
     "b200gf_hop_scatter": (c_int, [c_vp, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_int, PP, c_int, c_i64, c_i64, c_i64,
                                    c_int, c_i64, c_vp]),
     "b200gf_scatter_rows": (c_int, [c_int, c_vp, c_i64, c_i64, c_int, PP, c_int, c_i64, c_i64, c_i64, c_int, c_i64, c_vp]),
+    "b200gf_hop_bcast": (c_int, [c_vp, c_int, c_int, c_vp, c_i64, c_int, PP, c_int, c_vp, c_i64, c_i64, c_vp]),
+    "b200gf_bcast_rows": (c_int, [c_int, c_vp, c_i64, c_i64, c_int, PP, c_int, c_vp, c_i64, c_i64, c_vp]),
     "b200gf_symm_alloc": (c_int, [PP, c_sz]),
     "b200gf_symm_free": (c_int, [c_vp]),
     "b200gf_symm_export": (c_int, [c_vp, c_vp]),

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <atomic>
 #include <vector>
 
 #include "../../include/b200gf.h"
@@ -15,13 +16,18 @@
     if (_e != cudaSuccess) return B200GF_ECUDA - (int)_e;            \
   } while (0)
 
-#define LAUNCH_CHECK()                                               \
+// after every kernel launch (or group of n launches): error check + the library's launch counter (b200gf_launch_count)
+#define LAUNCH_CHECK_N(n)                                            \
   do {                                                               \
     cudaError_t _e = cudaGetLastError();                             \
     if (_e != cudaSuccess) return B200GF_ECUDA - (int)_e;            \
+    b200gf::g_launch_count.fetch_add((n), std::memory_order_relaxed); \
   } while (0)
+#define LAUNCH_CHECK() LAUNCH_CHECK_N(1)
 
 namespace b200gf {
+
+extern std::atomic<long long> g_launch_count;  // kernels launched by this library in this process (plan.cu)
 
 struct CsrDev {
   int64_t* rowptr = nullptr;  // [n_rows + 1]
@@ -49,11 +55,22 @@ struct ScatterHost {
   int gl, n_peers;
 };
 
+// type-erased description of the fused all-gather epilogue (spmm_kernels.cuh: BcastArgs)
+struct BcastHost {
+  void* peer[16];
+  void* mc;
+  int64_t row0, out_ld;
+  int n_peers;
+};
+
 // internal launchers (defined across the .cu files) -------------------------------------------------
 int launch_hop(int dtype, int sm_count, const CsrDev& A, int64_t n_rows, const void* src, int64_t src_ld,
-               void* dst, int64_t dst_ld, int C, cudaStream_t st, const ScatterHost* sh = nullptr);
+               void* dst, int64_t dst_ld, int C, cudaStream_t st, const ScatterHost* sh = nullptr,
+               const BcastHost* bh = nullptr);
 int launch_scatter_rows(int dtype, const void* src, int64_t src_ld, int64_t n_rows, int C, cudaStream_t st,
                         const ScatterHost* sh);
+int launch_bcast_rows(int dtype, const void* src, int64_t src_ld, int64_t n_rows, int C, cudaStream_t st,
+                      const BcastHost* bh);
 
 struct TermList {            // passed by value to kernels: up to MAX_TERMS (pointer, ld) pairs
   static constexpr int MAX_TERMS = 48;
@@ -112,5 +129,5 @@ struct b200gf_plan {
 namespace b200gf {
 // hop launch of forward/backward, bracketed with events when profiling is on
 int plan_hop(const b200gf_plan* p, const CsrDev& A, const void* src, int64_t src_ld, void* dst, int64_t dst_ld, int C,
-             cudaStream_t st, const ScatterHost* sh = nullptr);
+             cudaStream_t st, const ScatterHost* sh = nullptr, const BcastHost* bh = nullptr);
 }

@@ -86,10 +86,10 @@ bool bad_layout(int l) { return l != B200GF_FEATURE_MAJOR && l != B200GF_NODE_MA
 
 namespace b200gf {
 int plan_hop(const b200gf_plan* p, const CsrDev& A, const void* src, int64_t src_ld, void* dst, int64_t dst_ld, int C,
-             cudaStream_t st, const ScatterHost* sh) {
+             cudaStream_t st, const ScatterHost* sh, const BcastHost* bh) {
   const bool prof = p->prof_used < (int)p->prof_start.size();
   if (prof) CUDA_TRY(cudaEventRecord(p->prof_start[p->prof_used], st));
-  const int rc = launch_hop(p->dtype, p->sm_count, A, p->n_rows, src, src_ld, dst, dst_ld, C, st, sh);
+  const int rc = launch_hop(p->dtype, p->sm_count, A, p->n_rows, src, src_ld, dst, dst_ld, C, st, sh, bh);
   if (prof) {
     CUDA_TRY(cudaEventRecord(p->prof_stop[p->prof_used], st));
     p->prof_used++;

@@ -8,6 +8,10 @@
 
 using namespace b200gf;
 
+namespace b200gf {
+std::atomic<long long> g_launch_count{0};
+}
+
 namespace {
 
 struct HostCsr {
@@ -134,6 +138,10 @@ void free_csr(CsrDev& D) {
 extern "C" {
 
 int b200gf_version(void) { return B200GF_VERSION; }
+
+int64_t b200gf_launch_count(int reset) {
+  return reset ? g_launch_count.exchange(0, std::memory_order_relaxed) : g_launch_count.load(std::memory_order_relaxed);
+}
 
 const char* b200gf_strerror(int rc) {
   switch (rc) {

@@ -36,6 +36,15 @@ static ScatterArgs<T> make_scatter(const ScatterHost* sh) {
   return sc;
 }
 
+template <typename T>
+static BcastArgs<T> make_bcast(const BcastHost* bh) {
+  BcastArgs<T> bc{};
+  for (int i = 0; i < bh->n_peers; ++i) bc.peer[i] = reinterpret_cast<T*>(bh->peer[i]);
+  bc.mc = reinterpret_cast<T*>(bh->mc);
+  bc.row0 = bh->row0; bc.out_ld = bh->out_ld; bc.n_peers = bh->n_peers;
+  return bc;
+}
+
 // Library configuration, chosen from tools/spmm_sweep.cu on B200 (profiles/r1_spmm_sweep.md): 256 threads,
 // registers capped for 6 resident blocks/SM (48 warps: the kernel is latency-bound below that), gathered rows loaded
 // with an L2 evict_last policy and no L1 allocation (DRAM reads 7.9 GB -> 6.3 GB per hop at N=1M, C=64), no
@@ -86,9 +95,9 @@ static int launch_multirow(int sm_count, const CsrDev& A, int64_t n_rows, const 
 // Round-2 kernel (spmm_kernels.cuh: spmm_hop_v2_kernel): 32-byte lanes (LDG.E.256), 32-bit index arithmetic, no spills.
 // L lanes x 32 bytes cover a row chunk; 32/L neighbours per warp-wide load, U loads in flight per lane; 4 blocks of 256
 // threads per SM (64 registers); column chunks on blockIdx.y.  Sweep: profiles/r2_spmm_sweep*.log.
-template <typename T, int L, bool SCATTER>
+template <typename T, int L, int SCATTER>
 static int launch_v2(int sm_count, const CsrDev& A, int64_t n_rows, const T* src, int64_t src_ld, T* dst, int64_t dst_ld,
-                     int C, cudaStream_t st, const ScatterHost* sh) {
+                     int C, cudaStream_t st, const ScatterHost* sh, const BcastHost* bh) {
   constexpr int VEC = 32 / sizeof(T), U = 4, THREADS = 256, MINB = sizeof(T) == 4 ? 4 : 3, HINT = B200GF_HOP_L2_HINT;
   auto kern = spmm_hop_v2_kernel<T, int32_t, VEC, L, U, THREADS, MINB, HINT, SCATTER>;
   if (n_rows == 0) return B200GF_OK;
@@ -104,7 +113,8 @@ static int launch_v2(int sm_count, const CsrDev& A, int64_t n_rows, const T* src
   const int64_t cap = (int64_t)sm_count * occ;
   if (blocks > cap) blocks = cap;
   ScatterParam<T, SCATTER> sp{};
-  if constexpr (SCATTER) sp.a = make_scatter<T>(sh);
+  if constexpr (SCATTER == EPI_SCATTER) sp.a = make_scatter<T>(sh);
+  if constexpr (SCATTER == EPI_BCAST) sp.a = make_bcast<T>(bh);
   kern<<<dim3((unsigned)blocks, (unsigned)n_chunks), THREADS, 0, st>>>(A.rowptr32, A.col, reinterpret_cast<const T*>(A.val),
                                                                       src, (int)src_ld, dst, (int)dst_ld, (int)n_rows, C,
                                                                       B200GF_HOP_L2_FRAC, sp);
@@ -114,17 +124,32 @@ static int launch_v2(int sm_count, const CsrDev& A, int64_t n_rows, const T* src
 
 template <typename T, int L>
 static int launch_v2_sc(int sm_count, const CsrDev& A, int64_t n_rows, const T* src, int64_t src_ld, T* dst,
-                        int64_t dst_ld, int C, cudaStream_t st, const ScatterHost* sh) {
-  if (sh && sh->n_peers > 0) return launch_v2<T, L, true>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);
-  return launch_v2<T, L, false>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, nullptr);
+                        int64_t dst_ld, int C, cudaStream_t st, const ScatterHost* sh, const BcastHost* bh) {
+  if (bh) return launch_v2<T, L, EPI_BCAST>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, nullptr, bh);
+  if (sh && sh->n_peers > 0) return launch_v2<T, L, EPI_SCATTER>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh, nullptr);
+  return launch_v2<T, L, EPI_NONE>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, nullptr, nullptr);
 }
 
 template <typename T>
 static int launch_typed(int sm_count, const CsrDev& A, int64_t n_rows, const void* src_, int64_t src_ld,
-                        void* dst_, int64_t dst_ld, int C, cudaStream_t st, const ScatterHost* sh) {
+                        void* dst_, int64_t dst_ld, int C, cudaStream_t st, const ScatterHost* sh, const BcastHost* bh) {
   constexpr int VEC = 16 / sizeof(T);
   const T* src = reinterpret_cast<const T*>(src_);
   T* dst = reinterpret_cast<T*>(dst_);
+  if (bh) {
+    // fused all-gather epilogue: only the v2 kernel has it (32-byte aligned rows on both sides, 32-bit offsets)
+    constexpr int VWb = 32 / sizeof(T);
+    const int Cwb = (C + VWb - 1) / VWb * VWb;
+    bool ok = A.rowptr32 != nullptr && src_ld % VWb == 0 && Cwb <= src_ld && Cwb <= bh->out_ld && bh->out_ld % VWb == 0 &&
+              (reinterpret_cast<uintptr_t>(src) & 31) == 0 && src_ld <= INT32_MAX && n_rows <= INT32_MAX;
+    for (int i = 0; i < bh->n_peers; ++i) ok = ok && (reinterpret_cast<uintptr_t>(bh->peer[i]) & 31) == 0;
+    ok = ok && (reinterpret_cast<uintptr_t>(bh->mc) & 31) == 0;
+    if (!ok) return B200GF_EUNSUPPORTED;
+    const int nwb = Cwb / VWb;
+    if (nwb <= 8) return launch_v2_sc<T, 8>(sm_count, A, n_rows, src, src_ld, nullptr, 0, C, st, nullptr, bh);
+    if (nwb <= 16) return launch_v2_sc<T, 16>(sm_count, A, n_rows, src, src_ld, nullptr, 0, C, st, nullptr, bh);
+    return launch_v2_sc<T, 32>(sm_count, A, n_rows, src, src_ld, nullptr, 0, C, st, nullptr, bh);
+  }
   const int Cv = (C + VEC - 1) / VEC * VEC;
   const bool vec_ok = (src_ld % VEC == 0) && (dst_ld % VEC == 0) && (Cv <= src_ld) && (Cv <= dst_ld) &&
                       ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
@@ -150,21 +175,54 @@ static int launch_typed(int sm_count, const CsrDev& A, int64_t n_rows, const voi
     wide_ok = wide_ok && sh->gl % VW == 0 && sh->out_ld % VW == 0 && sh->out_col % VW == 0 && sh->stride_b % VW == 0;
   if (wide_ok) {
     const int nw = Cw / VW;  // 32-byte vectors per row
-    if (nw <= 8) return launch_v2_sc<T, 8>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);
-    if (nw <= 16) return launch_v2_sc<T, 16>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);
-    return launch_v2_sc<T, 32>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);
+    if (nw <= 8) return launch_v2_sc<T, 8>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh, nullptr);
+    if (nw <= 16) return launch_v2_sc<T, 16>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh, nullptr);
+    return launch_v2_sc<T, 32>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh, nullptr);
   }
   if (nv <= 16) return launch_one<T, VEC, 16, 4>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);
   return launch_one<T, VEC, 32, 4>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);
 }
 
 int launch_hop(int dtype, int sm_count, const CsrDev& A, int64_t n_rows, const void* src, int64_t src_ld,
-               void* dst, int64_t dst_ld, int C, cudaStream_t st, const ScatterHost* sh) {
-  if (C <= 0 || src_ld < C || dst_ld < C) return B200GF_EINVAL;
+               void* dst, int64_t dst_ld, int C, cudaStream_t st, const ScatterHost* sh, const BcastHost* bh) {
+  if (C <= 0 || src_ld < C || (!bh && dst_ld < C)) return B200GF_EINVAL;
   if (sh && (sh->n_peers < 0 || sh->n_peers > MAX_PEERS)) return B200GF_EINVAL;
-  if (dtype == B200GF_F32) return launch_typed<float>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);
-  if (dtype == B200GF_F64) return launch_typed<double>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);
+  if (bh && (bh->n_peers <= 0 || bh->n_peers > MAX_PEERS || bh->out_ld < C || sh)) return B200GF_EINVAL;
+  if (dtype == B200GF_F32) return launch_typed<float>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh, bh);
+  if (dtype == B200GF_F64) return launch_typed<double>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh, bh);
   return B200GF_EUNSUPPORTED;
+}
+
+// all-gather of an existing node-major row block (the k = 0 term x): every rank's full-height matrix gets these rows
+template <typename T, int VEC>
+__global__ void bcast_rows_kernel(const T* __restrict__ src, int64_t src_ld, int64_t n_rows, int C, const BcastArgs<T> bc) {
+  const int vpr = C / VEC;
+  const int64_t total = n_rows * vpr;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / vpr;
+    const int cbase = (int)(i - row * vpr) * VEC;
+    const Acc<T, VEC> a = load_vec<T, VEC, 0>(src + row * src_ld + cbase, 0);
+    bcast_store<T, VEC>(bc, row, cbase, a);
+  }
+}
+
+int launch_bcast_rows(int dtype, const void* src, int64_t src_ld, int64_t n_rows, int C, cudaStream_t st,
+                      const BcastHost* bh) {
+  if (!src || !bh || bh->n_peers <= 0 || bh->n_peers > MAX_PEERS || C <= 0 || src_ld < C || bh->out_ld < C) return B200GF_EINVAL;
+  if (n_rows == 0) return B200GF_OK;
+  const int blocks = 148 * 8;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(bh->mc) & 15)) return B200GF_EUNSUPPORTED;
+  if (dtype == B200GF_F32) {
+    if (C % 4 || src_ld % 4 || bh->out_ld % 4) return B200GF_EUNSUPPORTED;
+    bcast_rows_kernel<float, 4><<<blocks, 256, 0, st>>>((const float*)src, src_ld, n_rows, C, make_bcast<float>(bh));
+  } else if (dtype == B200GF_F64) {
+    if (C % 2 || src_ld % 2 || bh->out_ld % 2) return B200GF_EUNSUPPORTED;
+    bcast_rows_kernel<double, 2><<<blocks, 256, 0, st>>>((const double*)src, src_ld, n_rows, C, make_bcast<double>(bh));
+  } else {
+    return B200GF_EUNSUPPORTED;
+  }
+  LAUNCH_CHECK();
+  return B200GF_OK;
 }
 
 // copy-scatter of an existing node-major matrix (the k = 0 term, x itself) into the peers' row-local operands
@@ -248,6 +306,39 @@ extern "C" int b200gf_scatter_rows(int dtype, const void* src, int64_t src_ld, i
   if (rc) return rc;
   if (n_rows > rows_per_peer * n_peers || C % gl != 0) return B200GF_EINVAL;
   return b200gf::launch_scatter_rows(dtype, src, src_ld, n_rows, C, (cudaStream_t)stream, &sh);
+}
+
+static int fill_bcast(b200gf::BcastHost& bh, const void* const* peers, int n_peers, const void* mc, int64_t row0, int64_t out_ld) {
+  if (!peers || n_peers <= 0 || n_peers > b200gf::MAX_PEERS || row0 < 0 || out_ld <= 0) return B200GF_EINVAL;
+  for (int i = 0; i < n_peers; ++i) {
+    if (!peers[i]) return B200GF_EINVAL;
+    bh.peer[i] = const_cast<void*>(peers[i]);
+  }
+  bh.mc = const_cast<void*>(mc);
+  bh.n_peers = n_peers; bh.row0 = row0; bh.out_ld = out_ld;
+  return B200GF_OK;
+}
+
+extern "C" int b200gf_hop_bcast(const b200gf_plan* plan, int e, int direction, const void* src, int64_t src_ld, int C,
+                                const void* const* peers, int n_peers, const void* mc, int64_t row0, int64_t out_ld,
+                                void* stream) {
+  if (!plan || !src || e < 0 || e >= plan->E) return B200GF_EINVAL;
+  if (direction != B200GF_HOP_FWD && direction != B200GF_HOP_BWD) return B200GF_EINVAL;
+  if (direction == B200GF_HOP_BWD && !plan->has_bwd) return B200GF_EINVAL;
+  b200gf::BcastHost bh{};
+  int rc = fill_bcast(bh, peers, n_peers, mc, row0, out_ld);
+  if (rc) return rc;
+  const b200gf::CsrDev& A = direction == B200GF_HOP_FWD ? plan->fwd[e] : plan->bwd[e];
+  return b200gf::plan_hop(plan, A, src, src_ld, nullptr, 0, C, (cudaStream_t)stream, nullptr, &bh);
+}
+
+extern "C" int b200gf_bcast_rows(int dtype, const void* src, int64_t src_ld, int64_t n_rows, int C,
+                                 const void* const* peers, int n_peers, const void* mc, int64_t row0, int64_t out_ld,
+                                 void* stream) {
+  b200gf::BcastHost bh{};
+  int rc = fill_bcast(bh, peers, n_peers, mc, row0, out_ld);
+  if (rc) return rc;
+  return b200gf::launch_bcast_rows(dtype, src, src_ld, n_rows, C, (cudaStream_t)stream, &bh);
 }
 
 extern "C" int b200gf_symm_alloc(void** ptr, size_t bytes) {

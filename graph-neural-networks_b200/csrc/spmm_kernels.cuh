@@ -288,14 +288,58 @@ spmm_hop_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ 
 //     A unit is a row (or a SLOTS-neighbour segment of a longer row).  Every lane reads back exactly the 16 bytes it
 //     copied itself, so no barrier is needed: cp.async.wait_group is the only synchronisation.
 // ---------------------------------------------------------------------------------------------------
-template <typename T, bool ON>
-struct ScatterParam { ScatterArgs<T> a; };
+// Fused hop + all-gather (node-sharded multi-GPU path): the rank computes rows [row0, row0 + n_rows) of the next hop's
+// source matrix and every finished row is written into the full-height matrix of EVERY rank while the gather of the
+// following rows is still in flight — either with one multimem.st through the NVSwitch multicast address `mc`
+// (egress n_rows*C*s per hop) or, without multicast, with one NVLink peer store per rank (egress (P-1)/P*N*C*s).
 template <typename T>
-struct ScatterParam<T, false> {};
+struct BcastArgs {
+  T* peer[MAX_PEERS];     // full-height destination [n_total, out_ld] of every rank (own one included)
+  T* mc;                  // multicast alias of the same buffer, or nullptr
+  int64_t row0;           // global index of this rank's first row
+  int64_t out_ld;
+  int n_peers;
+};
+
+template <int VEC>
+__device__ __forceinline__ void multimem_store(float* p, const Acc<float, VEC>& a) {
+#pragma unroll
+  for (int i = 0; i < VEC; i += 4)
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p + i), "f"(a.v[i]), "f"(a.v[i + 1]),
+                 "f"(a.v[i + 2]), "f"(a.v[i + 3]) : "memory");
+}
+template <int VEC>
+__device__ __forceinline__ void multimem_store(double* p, const Acc<double, VEC>& a) {
+  // multimem.st has no f64 vector form; a store moves bits, so two doubles travel as one .v4.f32
+#pragma unroll
+  for (int i = 0; i < VEC; i += 2)
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p + i),
+                 "f"(__int_as_float(__double2loint(a.v[i]))), "f"(__int_as_float(__double2hiint(a.v[i]))),
+                 "f"(__int_as_float(__double2loint(a.v[i + 1]))), "f"(__int_as_float(__double2hiint(a.v[i + 1]))) : "memory");
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ void bcast_store(const BcastArgs<T>& bc, int64_t row, int cbase, const Acc<T, VEC>& acc) {
+  const int64_t off = (bc.row0 + row) * bc.out_ld + cbase;
+  if (bc.mc != nullptr) {
+    multimem_store<VEC>(bc.mc + off, acc);
+  } else {
+    for (int q = 0; q < bc.n_peers; ++q) store_vec<T, VEC, 0>(bc.peer[q] + off, acc);
+  }
+}
+
+// epilogue of the v2 / async kernels.  MODE 0: plain hop; 1: feature-sharded scatter (ScatterArgs); 2: row broadcast.
+constexpr int EPI_NONE = 0, EPI_SCATTER = 1, EPI_BCAST = 2;
+template <typename T, int MODE>
+struct ScatterParam {};
+template <typename T>
+struct ScatterParam<T, EPI_SCATTER> { ScatterArgs<T> a; };
+template <typename T>
+struct ScatterParam<T, EPI_BCAST> { BcastArgs<T> a; };
 
 // HINT: 0/1 no L2 policy; 3 evict_last on every gathered line; 2 evict_last on the fraction l2_frac of the lines (by
 // address hash), the rest unchanged; 6 the same with evict_first on the rest.  SH = 1: streaming stores of the result.
-template <typename T, typename IDX, int VEC, int L, int U, int THREADS, int MINB, int HINT, bool SCATTER, int SH = 0>
+template <typename T, typename IDX, int VEC, int L, int U, int THREADS, int MINB, int HINT, int SCATTER, int SH = 0>
 __global__ void __launch_bounds__(THREADS, MINB)
 spmm_hop_v2_kernel(const IDX* __restrict__ rowptr, const int32_t* __restrict__ col, const T* __restrict__ val,
                    const T* __restrict__ src, int src_ld, T* __restrict__ dst, int dst_ld, int n_rows, int C,
@@ -357,9 +401,13 @@ spmm_hop_v2_kernel(const IDX* __restrict__ rowptr, const int32_t* __restrict__ c
       asm volatile("mov.u32 %0, %%laneid;" : "=r"(ln));
       asm volatile("mov.u32 %0, %%nctaid.x;" : "=r"(gdx));
       if (ln < (unsigned)L && cbase < C) {
-        store_vec<T, VEC, SH>(dst + (int64_t)row * dst_ld + cbase, acc);
-        if constexpr (SCATTER) {
-          if (sp.a.n_peers > 0) scatter_store<T, VEC>(sp.a, row, cbase, acc);
+        if constexpr (SCATTER == EPI_BCAST) {
+          bcast_store<T, VEC>(sp.a, row, cbase, acc);        // the rank's own copy is one of the destinations
+        } else {
+          store_vec<T, VEC, SH>(dst + (int64_t)row * dst_ld + cbase, acc);
+          if constexpr (SCATTER == EPI_SCATTER) {
+            if (sp.a.n_peers > 0) scatter_store<T, VEC>(sp.a, row, cbase, acc);
+          }
         }
       }
       row += (int)gdx * (THREADS >> 5);
@@ -378,7 +426,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // shared memory per warp: 2 * SLOTS * L * 16 bytes
-template <typename T, typename IDX, int VEC, int L, int SLOTS, int THREADS, int MINB, int HINT, bool SCATTER>
+template <typename T, typename IDX, int VEC, int L, int SLOTS, int THREADS, int MINB, int HINT, int SCATTER>
 __global__ void __launch_bounds__(THREADS, MINB)
 spmm_hop_async_kernel(const IDX* __restrict__ rowptr, const int32_t* __restrict__ col, const T* __restrict__ val,
                       const T* __restrict__ src, int src_ld, T* __restrict__ dst, int dst_ld, int n_rows, int C,
@@ -530,9 +578,13 @@ spmm_hop_async_kernel(const IDX* __restrict__ rowptr, const int32_t* __restrict_
           for (int i = 0; i < VEC; ++i) r.v[i] += __shfl_xor_sync(FULL, r.v[i], off);
         }
         if (sub == 0 && col_ok) {
-          store_vec<T, VEC, 0>(dst + (int64_t)u0.row * dst_ld + cbase, r);
-          if constexpr (SCATTER) {
-            if (sp.a.n_peers > 0) scatter_store<T, VEC>(sp.a, u0.row, cbase, r);
+          if constexpr (SCATTER == EPI_BCAST) {
+            bcast_store<T, VEC>(sp.a, u0.row, cbase, r);
+          } else {
+            store_vec<T, VEC, 0>(dst + (int64_t)u0.row * dst_ld + cbase, r);
+            if constexpr (SCATTER == EPI_SCATTER) {
+              if (sp.a.n_peers > 0) scatter_store<T, VEC>(sp.a, u0.row, cbase, r);
+            }
           }
         }
       }

@@ -577,7 +577,7 @@ int launch_bias_grad(int dtype, int64_t n_rows, int B, int F, const void* dy, in
       bias_grad_partial_kernel<double><<<n_chunks, 256, 0, st>>>((const double*)dy, dy_ld, n_rows, B, F, (double*)scratch);
     bias_grad_reduce_kernel<double><<<(F + 127) / 128, 128, 0, st>>>((const double*)scratch, n_chunks, F, (double*)dbias);
   }
-  LAUNCH_CHECK();
+  LAUNCH_CHECK_N(n_chunks > 0 ? 2 : 1);
   return B200GF_OK;
 }
 

@@ -80,6 +80,14 @@ class CudaOps:
                                                  _cabi.ptr_array(peers), len(peers), rows_per_peer, out_ld, out_col, gl,
                                                  stride_b, self._st()))
 
+    def hop_bcast(self, plan, e, direction, src, C, peers, mc, row0, out_ld):
+        _cabi.check(self.lib.b200gf_hop_bcast(plan.handle, e, direction, src.data_ptr(), src.stride(0), C,
+                                              _cabi.ptr_array(peers), len(peers), mc or None, row0, out_ld, self._st()))
+
+    def bcast_rows(self, src, n_rows, C, peers, mc, row0, out_ld):
+        _cabi.check(self.lib.b200gf_bcast_rows(_ENUM[src.dtype], src.data_ptr(), src.stride(0), n_rows, C,
+                                               _cabi.ptr_array(peers), len(peers), mc or None, row0, out_ld, self._st()))
+
     def pack_taps(self, h, transpose):
         F, E, K, G = h.shape
         T = 1 + E * (K - 1)
@@ -122,6 +130,96 @@ class _RawMat:
         return self._ld if i == 0 else 1
 
 
+class SymmetricArena:
+    """`nbytes` of device memory on every rank that all ranks of the node can address, plus the peer-flag fence state.
+
+    Plumbing only: the allocation and the address exchange go through torch.distributed's symmetric memory
+    (torch.distributed._symmetric_memory: cuMem allocations, peer mappings and — when the NVSwitch supports it — a
+    multicast alias), falling back to this library's CUDA-IPC calls (b200gf_symm_*: no multicast).  Everything that
+    touches the memory afterwards is this library's kernels: hop_bcast / bcast_rows stores, peer_signal / peer_wait.
+    Layout: [payload, 256-byte aligned][16 x u64 arrival flags][u64 local step counter]."""
+
+    def __init__(self, lib, nbytes, group, device, prefer="auto"):
+        import ctypes
+        self.lib, self.group, self.device = lib, group, torch.device(device)
+        self.payload = (int(nbytes) + 255) // 256 * 256
+        self.flags_off = self.payload
+        self.step_off = self.flags_off + 128
+        total = self.payload + 256
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.peers, self.mc, self.kind = None, 0, None
+        self._opened, self._own, self._keep = [], 0, None
+        if prefer in ("auto", "torch"):
+            try:
+                import torch.distributed._symmetric_memory as symm
+                t = symm.empty(total, dtype=torch.uint8, device=self.device)
+                t.zero_()
+                hdl = symm.rendezvous(t, group if group is not None else dist.group.WORLD)
+                self.peers = [int(p) for p in hdl.buffer_ptrs]
+                self.mc = int(hdl.multicast_ptr or 0)
+                self._keep = (t, hdl)
+                self.kind = "torch-symm" + ("+multicast" if self.mc else "")
+            except Exception as exc:                       # older driver / no fabric support: plain CUDA IPC below
+                if prefer == "torch":
+                    raise
+                self._why_not_torch = repr(exc)[:200]
+                self.peers = None
+        if self.peers is None:
+            mine = ctypes.c_void_p()
+            _cabi.check(lib.b200gf_symm_alloc(ctypes.byref(mine), total))      # zero-filled
+            self._own = mine.value
+            handle = (ctypes.c_ubyte * 64)()
+            _cabi.check(lib.b200gf_symm_export(ctypes.c_void_p(self._own), handle))
+            t = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=self.device)
+            allh = [torch.empty_like(t) for _ in range(self.world)]
+            dist.all_gather(allh, t, group=group)
+            self.peers = []
+            for p in range(self.world):
+                if p == self.rank:
+                    self.peers.append(self._own)
+                    continue
+                raw = (ctypes.c_ubyte * 64)(*allh[p].cpu().tolist())
+                ptr = ctypes.c_void_p()
+                _cabi.check(lib.b200gf_symm_import(raw, ctypes.byref(ptr)))
+                self.peers.append(ptr.value)
+                self._opened.append(ptr.value)
+            self.kind = "cuda-ipc"
+        self.mine = self.peers[self.rank]
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=group)                          # every rank's memory is zeroed before anyone signals into it
+
+    def peer_ptrs(self, offset):
+        return [p + offset for p in self.peers]
+
+    def mc_ptr(self, offset):
+        return self.mc + offset if self.mc else 0
+
+    def local(self, offset, ld):
+        return _RawMat(self.mine + offset, ld)
+
+    def fence(self, stream):
+        """signal + wait on the symmetric flag arrays: returns (on the stream) once every rank's earlier stores have landed."""
+        import ctypes
+        _cabi.check(self.lib.b200gf_peer_signal(_cabi.ptr_array([p + self.flags_off for p in self.peers]), self.world,
+                                                self.rank, ctypes.c_void_p(self.mine + self.step_off), stream))
+        _cabi.check(self.lib.b200gf_peer_wait(ctypes.c_void_p(self.mine + self.flags_off), self.world,
+                                              ctypes.c_void_p(self.mine + self.step_off), stream))
+
+    def close(self):
+        """Collective.  Nobody frees memory a peer may still have mapped: synchronise, barrier, unmap, barrier, free."""
+        import ctypes
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        for p in self._opened:
+            self.lib.b200gf_symm_close(ctypes.c_void_p(p))
+        self._opened = []
+        dist.barrier(group=self.group)
+        if self._own:
+            self.lib.b200gf_symm_free(ctypes.c_void_p(self._own))
+            self._own = 0
+        self._keep = None
+
+
 class SymmetricOperand:
     """Double-buffered row-local contraction operand [2][R, row_elems] that every peer can write over NVLink
     (b200gf_symm_* : cudaMalloc + CUDA IPC).  Double buffering removes the write-after-read hazard between a fast
@@ -129,7 +227,7 @@ class SymmetricOperand:
 
     def __init__(self, lib, R, row_elems, dtype, group, device):
         import ctypes
-        self.lib, self.R, self.row_elems = lib, R, row_elems
+        self.lib, self.R, self.row_elems, self.group = lib, R, row_elems, group
         es = 4 if dtype == torch.float32 else 8
         self.buf_bytes = (R * row_elems * es + 255) // 256 * 256
         # layout: [operand 0][operand 1][16 x u64 arrival flags][u64 local step counter]   (alloc zero-fills)
@@ -172,10 +270,15 @@ class SymmetricOperand:
                                               ctypes.c_void_p(self.mine + self.step_off), stream))
 
     def close(self):
+        """Collective: a peer may still have this buffer mapped, so synchronise + barrier before unmapping and again
+        before cudaFree (freeing IPC-exported memory that is still open elsewhere is undefined behaviour)."""
         import ctypes
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
         for p in self._opened:
             self.lib.b200gf_symm_close(ctypes.c_void_p(p))
         self._opened = []
+        dist.barrier(group=self.group)
         if self.mine:
             self.lib.b200gf_symm_free(ctypes.c_void_p(self.mine))
             self.mine = 0
@@ -189,14 +292,17 @@ class PartitionedLSIGF:
     In both, row block p covers global nodes [p*rows_per_rank, (p+1)*rows_per_rank) (the last block is zero-padded).
     """
 
-    def __init__(self, gso, mode="nodes", group=None, device=None, ops=None, fused=None, fence="flags"):
+    def __init__(self, gso, mode="nodes", group=None, device=None, ops=None, fused=None, fence="flags", symm_backend="auto"):
         assert mode in ("nodes", "features") and fence in ("flags", "nccl")
         self.mode = mode
+        self.symm_backend = symm_backend   # "auto": torch symmetric memory (multicast when available), else CUDA IPC; "ipc"; "torch"
         self.fence = fence          # "flags": peer flags in symmetric memory (no NCCL at all); "nccl": 4-byte all-reduce
         # fused = hop kernels scatter their rows over NVLink themselves (no NCCL collective on the data path);
         # default: on whenever the real CUDA ops run under NCCL with <= 16 ranks
         self._fused_req = fused
         self._symm = None
+        self._symm_by_width = {}
+        self._arenas = {}
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
@@ -221,7 +327,7 @@ class PartitionedLSIGF:
             self.plan = self.ops.make_plan_full(gso)
         self._bufs = {}
         if self._fused_req is None:
-            self.fused = (ops is None and mode == "features" and dist.get_backend(group) == "nccl" and self.world <= 16)
+            self.fused = (ops is None and dist.get_backend(group) == "nccl" and self.world <= 16)
         else:
             self.fused = bool(self._fused_req)
 
@@ -243,6 +349,8 @@ class PartitionedLSIGF:
     def forward(self, h, x_local, b=None, B=1):
         """B (batch size) is only read in features mode, where it cannot be inferred from an empty column slice."""
         if self.mode == "nodes":
+            if self.fused and self._nodes_fused_ok(x_local.shape[1]):
+                return self._forward_nodes_fused(h, x_local, b)
             return self._forward_nodes(h, x_local, b)
         return self._forward_features(h, x_local, b, B)
 
@@ -280,6 +388,89 @@ class PartitionedLSIGF:
             bias = b.contiguous()
         self.ops.tap_contract(zs, W, bias, y, R, B, G, F)
         return y[:, :B * F]
+
+    # -- node sharding with the all-gather fused into the hop kernel ------------------------------------
+    def _nodes_fused_ok(self, C):
+        q = 8 if self.dtype == torch.float32 else 4
+        return C * (4 if self.dtype == torch.float32 else 8) > 128 and _pad_ld(C, self.dtype) % q == 0
+
+    def _arena(self, key, n_bufs, ld):
+        """Symmetric arena of n_bufs full-height node-major matrices [n_pad, ld] (cached per shape)."""
+        a = self._arenas.get(key)
+        if a is None:
+            es = 4 if self.dtype == torch.float32 else 8
+            buf = (self.n_pad * ld * es + 255) // 256 * 256
+            a = SymmetricArena(self.ops.lib, n_bufs * buf, self.group, self.device, prefer=self.symm_backend)
+            a.buf_bytes = buf
+            self._arenas[key] = a
+        return a
+
+    def _chain_nodes_fused(self, direction, rows, E, K, key):
+        """[z_0 rows, z_{e,k} rows ...] (T node-major row blocks of this rank) for the shift chains of `rows`
+        ([rows_per_rank, C]) with the forward (z S_e) or backward (S_e z) operator.  Every hop that has a successor runs
+        b200gf_hop_bcast: its rows land in the full-height matrix of every rank (NVLink peer stores or one NVSwitch
+        multicast store per row) while the kernel is still gathering, a peer-flag fence separates the hops; the last hop
+        of a chain stays local.  No NCCL call, no host synchronisation."""
+        C = rows.shape[1]
+        ld = _pad_ld(C, self.dtype)
+        es = rows.element_size()
+        T = 1 + E * (K - 1)
+        R, r0 = self.rows_per_rank, self.r0
+        ar = self._arena((key, ld, T), T, ld)
+        st = self.ops._st()
+        local_rows = lambda t: ar.local(t * ar.buf_bytes + r0 * ld * es, ld)      # noqa: E731
+        local_full = lambda t: ar.local(t * ar.buf_bytes, ld)                     # noqa: E731
+        if K > 1:
+            self.ops.bcast_rows(rows, R, C, ar.peer_ptrs(0), ar.mc_ptr(0), r0, ld)   # all-gather of the k = 0 block
+            ar.fence(st)
+        out = [rows]
+        for e in range(E):
+            src = local_full(0)
+            for k in range(1, K):
+                t = 1 + e * (K - 1) + (k - 1)
+                if k < K - 1:
+                    self.ops.hop_bcast(self.plan, e, direction, src, C, ar.peer_ptrs(t * ar.buf_bytes),
+                                       ar.mc_ptr(t * ar.buf_bytes), r0, ld)
+                    ar.fence(st)
+                else:
+                    self.ops.hop(self.plan, e, direction, src, local_rows(t), C)
+                out.append(local_rows(t))
+                src = local_full(t)
+        return out
+
+    def _forward_nodes_fused(self, h, x_rows, b):
+        F, E, K, G = h.shape
+        C = x_rows.shape[1]
+        B = C // G
+        assert E == self.E and C == B * G and x_rows.shape[0] == self.rows_per_rank
+        R = self.rows_per_rank
+        if x_rows.stride(1) != 1 or (x_rows.stride(0) * x_rows.element_size()) % 16 or x_rows.data_ptr() % 16:
+            x_rows = x_rows.contiguous()
+        zs = self._chain_nodes_fused(_cabi.HOP_FWD, x_rows, E, K, "fwd")
+        W = self.ops.pack_taps(h, False)
+        y = torch.empty((R, _pad_ld(B * F, self.dtype)), dtype=self.dtype, device=self.device)
+        bias = None
+        if b is not None:
+            assert b.shape[1] == 1, "per-node bias is not supported by the partitioned path"
+            bias = b.contiguous()
+        self.ops.tap_contract(zs, W, bias, y, R, B, G, F)
+        return y[:, :B * F]
+
+    def _backward_nodes_fused(self, h, x_rows, dy_rows, want_db):
+        F, E, K, G = h.shape
+        R = self.rows_per_rank
+        C = x_rows.shape[1]
+        B = C // G
+        CF = B * F
+        if dy_rows.stride(1) != 1 or (dy_rows.stride(0) * dy_rows.element_size()) % 16 or dy_rows.data_ptr() % 16:
+            dy_rows = dy_rows.contiguous()
+        vs = self._chain_nodes_fused(_cabi.HOP_BWD, dy_rows, E, K, "bwd")     # V_{e,k} = S_e^k dY, my rows
+        dW = self.ops.tap_grad(x_rows, vs, R, B, G, F)                          # [T, G, F]
+        dist.all_reduce(dW, group=self.group)
+        dh = _unpack_tap_grads(dW.transpose(1, 2), E, K)
+        dx = torch.empty((R, _pad_ld(C, self.dtype)), dtype=self.dtype, device=self.device)
+        self.ops.tap_contract(vs, self.ops.pack_taps(h, True), None, dx, R, B, F, G)
+        return dh, dx[:, :C], (self._bias_grad(dy_rows, B, F) if want_db else None)
 
     def _forward_features(self, h, x_cols, b, B):
         """Column-sharded hops (no communication inside a hop) + an all-to-all of every shifted slice to the rank that
@@ -336,19 +527,24 @@ class PartitionedLSIGF:
         T = 1 + E * (K - 1)
         row_elems = B * T * G
         assert x_cols.shape[0] == self.N and x_cols.shape[1] == Cl
-        if self._symm is None or self._symm.row_elems != row_elems:
-            if self._symm is not None:
-                self._symm.close()
-            self._symm = SymmetricOperand(self.ops.lib, R, row_elems, self.dtype, self.group, self.device)
-            self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
-        sy = self._symm
+        sy = self._symm_by_width.get(row_elems)        # one operand per width: layers of different widths alternate
+        if sy is None:
+            sy = SymmetricOperand(self.ops.lib, R, row_elems, self.dtype, self.group, self.device)
+            self._symm_by_width[row_elems] = sy
+            if not hasattr(self, "_flag"):
+                self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._symm = sy
         buf = sy.step & 1
         sy.step += 1
         peers = sy.peer_ptrs(buf)
         g0 = self.rank * Gl
         ld = _pad_ld(Cl, self.dtype)
-        z0 = self._buffers(("fz0", Cl), (self.n_pad, ld))
-        z0[:self.N, :Cl].copy_(x_cols)
+        vecb = 16
+        if x_cols.stride(1) == 1 and (x_cols.stride(0) * x_cols.element_size()) % vecb == 0 and x_cols.data_ptr() % vecb == 0:
+            z0 = x_cols                                 # the caller's buffer is the k = 0 source: no staging copy
+        else:
+            z0 = self._buffers(("fz0", Cl), (self.n_pad, ld))
+            z0[:self.N, :Cl].copy_(x_cols)
         self.ops.scatter_rows(z0, self.N, Cl, peers, R, row_elems, g0, Gl, T * G)
         for e in range(E):
             src = z0
@@ -379,6 +575,8 @@ class PartitionedLSIGF:
         other operator (rows of S_e), exchanged like the forward's; dh and db end in one small all-reduce."""
         assert dy_rows.shape[0] == self.rows_per_rank
         if self.mode == "nodes":
+            if self.fused and self._nodes_fused_ok(x_local.shape[1]) and self._nodes_fused_ok(dy_rows.shape[1]):
+                return self._backward_nodes_fused(h, x_local, dy_rows, want_db)
             return self._backward_nodes(h, x_local, dy_rows, want_db)
         return self._backward_features(h, x_local, dy_rows, B, want_db)
 
@@ -502,13 +700,14 @@ class PartitionedLSIGF:
         are captured after two eager warm-up calls and replayed alternately, so a step costs one graph launch on the
         host.  Needs fence="flags" (everything in the step is then a kernel of this library or a device copy).
         Returns a callable; each call replays one step on the current contents of x_static / h / b."""
-        assert self.mode == "features" and self.fused and self.fence == "flags"
+        assert self.fused and self.fence == "flags"
         for _ in range(2):
             self.forward(h, x_static, b, B)
         torch.cuda.synchronize()
-        if self._symm is None:
-            raise RuntimeError("b200gf: graphed() needs the fused path (G/world a multiple of the 16-byte vector width)")
-        assert self._symm.step % 2 == 0
+        if self.mode == "features":
+            if self._symm is None:
+                raise RuntimeError("b200gf: graphed() needs the fused path (G/world a multiple of the 16-byte vector width)")
+            assert self._symm.step % 2 == 0
         graphs, outs = [], []
         for _ in range(2):
             g = torch.cuda.CUDAGraph()

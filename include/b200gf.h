@@ -57,6 +57,10 @@ enum {
 const char* b200gf_strerror(int rc);
 int b200gf_version(void);
 
+/* Number of CUDA kernels this library has launched in this process (every launch site counts itself); reset != 0
+ * returns the count and zeroes it.  bench.py reports it as `gpu_launches` for the timed region. */
+int64_t b200gf_launch_count(int reset);
+
 /* ------------------------------------------------------------------------------------------------
  * Plan = the device-resident sparse form of the GSO.  Replaces GraphFilter.addGSO (graphML.py:2116-2123),
  * which stores a dense E x N x N tensor.
@@ -150,6 +154,22 @@ int b200gf_hop_scatter(const b200gf_plan* plan, int e, int direction,
 int b200gf_scatter_rows(int dtype, const void* src, int64_t src_ld, int64_t n_rows, int C,
                         const void* const* peers, int n_peers, int64_t rows_per_peer,
                         int64_t out_ld, int64_t out_col, int gl, int64_t stride_b, void* stream);
+
+/* Fused hop + all-gather for the node-sharded multi-GPU path: the plan holds this rank's n_rows rows of
+ * the operator (b200gf_plan_create_ops, global column indices); every computed row r is written to row row0 + r of the
+ * full-height matrix [n_total, out_ld] of EVERY rank — `peers`: HOST array of n_peers (<= 16) device pointers to those
+ * matrices (own one included; b200gf_symm_import or any peer-mapped allocation), so the next hop can start as soon as a
+ * fence (b200gf_peer_signal / b200gf_peer_wait) has passed.  If `mc` is not NULL it is the NVSwitch multicast alias of
+ * the same buffers and each row is written once with multimem.st instead of n_peers stores.  Rows must be 32-byte
+ * aligned on both sides (src_ld, out_ld multiples of 8 floats / 4 doubles).  b200gf_bcast_rows does the same for an
+ * existing row block (the k = 0 term x). */
+int b200gf_hop_bcast(const b200gf_plan* plan, int e, int direction,
+                     const void* src, int64_t src_ld, int C,
+                     const void* const* peers, int n_peers, const void* mc,
+                     int64_t row0, int64_t out_ld, void* stream);
+int b200gf_bcast_rows(int dtype, const void* src, int64_t src_ld, int64_t n_rows, int C,
+                      const void* const* peers, int n_peers, const void* mc,
+                      int64_t row0, int64_t out_ld, void* stream);
 
 /* Symmetric buffers for the above: device memory that other processes of the same node can map (CUDA IPC).
  * alloc zero-fills; export writes a 64-byte handle to send to the peers (torch.distributed); import maps a peer's

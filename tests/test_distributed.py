@@ -80,7 +80,7 @@ def _case(N=203, B=2, G=6, F=8, K=4, E=2, seed=3):
     return mats, x, h, b
 
 
-def _worker(rank, world, port, backend, mode, dtype_name, result_q, G=6, backward=True):
+def _worker(rank, world, port, backend, mode, dtype_name, result_q, G=6, backward=True, F=8):
     import gnn_b200
     from gnn_b200.distributed import PartitionedLSIGF
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -96,7 +96,7 @@ def _worker(rank, world, port, backend, mode, dtype_name, result_q, G=6, backwar
         dist.init_process_group("gloo", rank=rank, world_size=world)
         ops = OracleOps()
     try:
-        mats, x, h, b = _case(G=G)
+        mats, x, h, b = _case(G=G, F=F)
         B, G, N = x.shape
         F = h.shape[0]
         gso = gnn_b200.SparseGSO.from_scipy(mats, dtype=dtype)
@@ -163,10 +163,10 @@ def _worker(rank, world, port, backend, mode, dtype_name, result_q, G=6, backwar
         dist.destroy_process_group()
 
 
-def _run(backend, mode, dtype_name, world=2, G=6, backward=True):
+def _run(backend, mode, dtype_name, world=2, G=6, backward=True, F=8):
     ctx = mp.get_context("spawn")
     q = ctx.SimpleQueue()
-    mp.spawn(_worker, args=(world, _free_port(), backend, mode, dtype_name, q, G, backward), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), backend, mode, dtype_name, q, G, backward, F), nprocs=world, join=True)
     return q.get()
 
 
@@ -192,11 +192,13 @@ def test_row_slice_and_padding():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode,G", [("nodes", 6), ("features", 6), ("features", 16)])
+@pytest.mark.parametrize("mode,G", [("nodes", 6), ("nodes", 48), ("features", 6), ("features", 16)])
 @pytest.mark.parametrize("dtype_name,tol", [("float32", 1e-4), ("float64", 1e-11)])
 def test_partitioned_nccl_world2(mode, G, dtype_name, tol):
-    """features/G = 6: NCCL all-to-all path; features/G = 16: the fused hop + NVLink scatter kernels (G/P = 8 columns
-    per rank, 16-byte vectors) writing into CUDA-IPC symmetric operands."""
+    """nodes/G = 6: narrow rows, NCCL all-gather per hop; nodes/G = 48: the hop kernel with the fused all-gather epilogue
+    (b200gf_hop_bcast: NVLink peer stores / NVSwitch multicast into symmetric memory, peer-flag fences, CUDA-graph replay);
+    features/G = 6: NCCL all-to-all path; features/G = 16: the fused hop + NVLink scatter kernels (G/P = 8 columns per
+    rank, 16-byte vectors) writing into CUDA-IPC symmetric operands."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     err = _run("nccl", mode, dtype_name, G=G, backward=False)    # backward over NCCL: tests/test_widen_distributed.py

@@ -116,9 +116,9 @@ template <int L, int U, int THREADS, int MINB, int HINT, int SH = 0>
 double run_v2w(const Problem& P, const char* name, int reps, double peak, float frac = 1.0f) {   // 256-bit loads (VEC = 8)
   const int n_chunks = (P.C + L * 8 - 1) / (L * 8);
   const int64_t maxb = ((int64_t)P.N + THREADS / 32 - 1) / (THREADS / 32);
-  auto kern = spmm_hop_v2_kernel<float, int32_t, 8, L, U, THREADS, MINB, HINT, false, SH>;
+  auto kern = spmm_hop_v2_kernel<float, int32_t, 8, L, U, THREADS, MINB, HINT, 0, SH>;
   return time_variant(P, name, reps, peak, kern, THREADS, 0, 0, maxb, [&](unsigned blocks) {
-    kern<<<dim3(blocks, n_chunks), THREADS>>>(P.rowptr32, P.col, P.val, P.src, P.C, P.dst, P.C, (int)P.N, P.C, frac, ScatterParam<float, false>{});
+    kern<<<dim3(blocks, n_chunks), THREADS>>>(P.rowptr32, P.col, P.val, P.src, P.C, P.dst, P.C, (int)P.N, P.C, frac, ScatterParam<float, 0>{});
   });
 }
 
@@ -127,14 +127,14 @@ double run_v2(const Problem& P, const char* name, int reps, double peak) {
   const int n_chunks = (P.C + L * 4 - 1) / (L * 4);
   const int64_t maxb = ((int64_t)P.N + THREADS / 32 - 1) / (THREADS / 32);
   if constexpr (I32) {
-    auto kern = spmm_hop_v2_kernel<float, int32_t, 4, L, U, THREADS, MINB, HINT, false>;
+    auto kern = spmm_hop_v2_kernel<float, int32_t, 4, L, U, THREADS, MINB, HINT, 0>;
     return time_variant(P, name, reps, peak, kern, THREADS, 0, 0, maxb, [&](unsigned blocks) {
-      kern<<<dim3(blocks, n_chunks), THREADS>>>(P.rowptr32, P.col, P.val, P.src, P.C, P.dst, P.C, (int)P.N, P.C, 1.0f, ScatterParam<float, false>{});
+      kern<<<dim3(blocks, n_chunks), THREADS>>>(P.rowptr32, P.col, P.val, P.src, P.C, P.dst, P.C, (int)P.N, P.C, 1.0f, ScatterParam<float, 0>{});
     });
   } else {
-    auto kern = spmm_hop_v2_kernel<float, int64_t, 4, L, U, THREADS, MINB, HINT, false>;
+    auto kern = spmm_hop_v2_kernel<float, int64_t, 4, L, U, THREADS, MINB, HINT, 0>;
     return time_variant(P, name, reps, peak, kern, THREADS, 0, 0, maxb, [&](unsigned blocks) {
-      kern<<<dim3(blocks, n_chunks), THREADS>>>(P.rowptr, P.col, P.val, P.src, P.C, P.dst, P.C, (int)P.N, P.C, 1.0f, ScatterParam<float, false>{});
+      kern<<<dim3(blocks, n_chunks), THREADS>>>(P.rowptr, P.col, P.val, P.src, P.C, P.dst, P.C, (int)P.N, P.C, 1.0f, ScatterParam<float, 0>{});
     });
   }
 }
@@ -145,9 +145,9 @@ double run_async(const Problem& P, const char* name, int reps, double peak) {
   const size_t smem = (size_t)(THREADS / 32) * 2 * SLOTS * L * 16;
   const int64_t nblk = (P.N + 31) / 32;
   const int64_t maxb = (nblk + THREADS / 32 - 1) / (THREADS / 32);
-  auto kern = spmm_hop_async_kernel<float, int32_t, 4, L, SLOTS, THREADS, MINB, HINT, false>;
+  auto kern = spmm_hop_async_kernel<float, int32_t, 4, L, SLOTS, THREADS, MINB, HINT, 0>;
   return time_variant(P, name, reps, peak, kern, THREADS, smem, 0, maxb, [&](unsigned blocks) {
-    kern<<<dim3(blocks, n_chunks), THREADS, smem>>>(P.rowptr32, P.col, P.val, P.src, P.C, P.dst, P.C, (int)P.N, P.C, ScatterParam<float, false>{});
+    kern<<<dim3(blocks, n_chunks), THREADS, smem>>>(P.rowptr32, P.col, P.val, P.src, P.C, P.dst, P.C, (int)P.N, P.C, ScatterParam<float, 0>{});
   });
 }
 
