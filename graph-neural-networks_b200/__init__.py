@@ -5,7 +5,7 @@ The directory is called `graph-neural-networks_b200` (not a valid Python identif
 """
 from . import _cabi  # noqa: F401
 from .gso import SparseGSO, Plan, plan_for, clear_plan_cache  # noqa: F401
-from .graphML import LSIGF, GraphFilter, install, uninstall, to_node_major, to_feature_major, node_major_ld, padded_ld  # noqa: F401
+from .graphML import LSIGF, GraphFilter, install, uninstall, fuse_layers, to_node_major, to_feature_major, node_major_ld, padded_ld  # noqa: F401
 
 from .edgevariant import EVGF, EdgeVariantGF  # noqa: F401,E402
 from .pooling import MaxPoolLocal  # noqa: F401,E402
@@ -13,4 +13,4 @@ from .activations import MaxLocalActivation, MedianLocalActivation, NoActivation
 from .recurrent import GatedGRNN, HiddenState, TimeGatedHiddenState, NodeGatedHiddenState  # noqa: F401,E402
 from .delayed import LSIGF_DB, GraphFilter_DB  # noqa: F401,E402
 
-__all__ = ["EVGF", "EdgeVariantGF", "MaxPoolLocal", "LSIGF", "GraphFilter", "SparseGSO", "Plan", "plan_for", "install", "uninstall"]
+__all__ = ["EVGF", "EdgeVariantGF", "MaxPoolLocal", "LSIGF", "GraphFilter", "SparseGSO", "Plan", "plan_for", "install", "uninstall", "fuse_layers"]

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "libb200gf.so")
 F32, F64 = 0, 1
 FEATURE_MAJOR, NODE_MAJOR = 0, 1
 HOP_FWD, HOP_BWD = 0, 1
+ACT_NONE, ACT_RELU = 0, 1
 
 _lib = None
 
@@ -30,6 +31,11 @@ _SIGNATURES = {
     "b200gf_plan_info": (c_i64, [c_vp, c_int]),
     "b200gf_forward": (c_int, [c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_int, c_vp, c_int, c_i64, c_vp, c_sz,
                                c_int, c_int, c_int, c_int, c_vp]),
+    "b200gf_forward_act": (c_int, [c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_int, c_vp, c_int, c_i64, c_vp, c_sz,
+                                   c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "b200gf_relu_backward": (c_int, [c_int, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_vp]),
+    "b200gf_maxpool_forward": (c_int, [c_int, c_vp, c_i64, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_i64, c_vp, c_vp]),
+    "b200gf_maxpool_backward": (c_int, [c_int, c_vp, c_i64, c_vp, c_i64, c_int, c_vp, c_i64, c_i64, c_vp]),
     "b200gf_backward": (c_int, [c_vp, c_vp, c_int, c_i64, c_vp, c_int, c_i64, c_vp, c_vp, c_int, c_i64, c_vp, c_vp,
                                 c_int, c_vp, c_sz, c_int, c_int, c_int, c_int, c_vp]),
     "b200gf_workspace_bytes": (c_sz, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int]),

@@ -80,7 +80,7 @@ struct TermList {            // passed by value to kernels: up to MAX_TERMS (poi
 
 int launch_tap_contract(int dtype, int64_t n_rows, int B, int P, int Q, int T, const void* const* zs,
                         const int64_t* z_ld, const void* W, const void* bias, int bias_per_node,
-                        void* out, int64_t out_ld, int accumulate, cudaStream_t st);
+                        void* out, int64_t out_ld, int accumulate, cudaStream_t st, int act = 0);
 
 // out_mode 0: dW[t][p][q];  out_mode 1: taps layout dh[F=Q, E, K, G=P] with t=0 broadcast to every e (k=0)
 int launch_tap_grad(int dtype, int64_t n_rows, int B, int P, int Q, int T, const void* A, int64_t a_ld,
@@ -100,7 +100,7 @@ int launch_pack_taps_split(const void* h, void* whi_wlo, int F, int E, int K, in
 int launch_split_w(const void* W, void* whi_wlo, int T, int P, int Q, cudaStream_t st);
 int launch_tc_contract(int sm_count, int64_t n_rows, int B, int P, int Q, int T, const void* const* zs,
                        const void* whi_wlo, const void* bias, int bias_per_node, void* out, int64_t out_ld,
-                       cudaStream_t st);
+                       cudaStream_t st, int act = 0);
 
 int launch_pack_taps(int dtype, const void* h, void* W, int F, int E, int K, int G, int transpose_taps,
                      cudaStream_t st);

@@ -134,9 +134,10 @@ size_t b200gf_workspace_bytes(const b200gf_plan* plan, int B, int G, int F, int 
   return carve_fwd(plan, nullptr, B, G, F, K, in_layout, in_layout).bytes + 256;
 }
 
-int b200gf_forward(const b200gf_plan* plan, const void* x, int x_layout, int64_t x_ld, const void* h,
-                   const void* bias, int bias_per_node, void* y, int y_layout, int64_t y_ld, void* workspace,
-                   size_t workspace_bytes, int B, int G, int F, int K, void* stream) {
+static int forward_impl(const b200gf_plan* plan, const void* x, int x_layout, int64_t x_ld, const void* h,
+                        const void* bias, int bias_per_node, void* y, int y_layout, int64_t y_ld, void* workspace,
+                        size_t workspace_bytes, int B, int G, int F, int K, int act, void* stream) {
+  if (act != B200GF_ACT_NONE && act != B200GF_ACT_RELU) return B200GF_EINVAL;
   if (!plan || !x || !h || !y || B <= 0 || G <= 0 || F <= 0 || K <= 0) return B200GF_EINVAL;
   if (bad_layout(x_layout) || bad_layout(y_layout)) return B200GF_EINVAL;
   if (plan->n_rows != plan->n_cols) return B200GF_EINVAL;  // partitioned plans use the building blocks
@@ -188,16 +189,30 @@ int b200gf_forward(const b200gf_plan* plan, const void* x, int x_layout, int64_t
   if (tc_contract_eligible(dt, N, B, G, F, T, zs.data(), zld.data(), yo, yo_ld, 0)) {
     // tensor cores: tcgen05 3xTF32, operands K-major: W[t][f][g]
     if ((rc = launch_pack_taps_split(h, w.W, F, E, K, G, 0, st))) return rc;
-    if ((rc = launch_tc_contract(plan->sm_count, N, B, G, F, T, zs.data(), w.W, bias, bias_per_node, yo, yo_ld, st)))
+    if ((rc = launch_tc_contract(plan->sm_count, N, B, G, F, T, zs.data(), w.W, bias, bias_per_node, yo, yo_ld, st, act)))
       return rc;
   } else {
     if ((rc = launch_pack_taps(dt, h, w.W, F, E, K, G, 0, st))) return rc;
-    if ((rc = launch_tap_contract(dt, N, B, G, F, T, zs.data(), zld.data(), w.W, bias, bias_per_node, yo, yo_ld, 0, st)))
+    if ((rc = launch_tap_contract(dt, N, B, G, F, T, zs.data(), zld.data(), w.W, bias, bias_per_node, yo, yo_ld, 0, st, act)))
       return rc;
   }
   if (y_layout == B200GF_FEATURE_MAJOR)
     if ((rc = launch_to_feature_major(dt, w.yn, ldf, y, N, (int)CF, st))) return rc;
   return B200GF_OK;
+}
+
+int b200gf_forward(const b200gf_plan* plan, const void* x, int x_layout, int64_t x_ld, const void* h,
+                   const void* bias, int bias_per_node, void* y, int y_layout, int64_t y_ld, void* workspace,
+                   size_t workspace_bytes, int B, int G, int F, int K, void* stream) {
+  return forward_impl(plan, x, x_layout, x_ld, h, bias, bias_per_node, y, y_layout, y_ld, workspace, workspace_bytes, B, G,
+                      F, K, B200GF_ACT_NONE, stream);
+}
+
+int b200gf_forward_act(const b200gf_plan* plan, const void* x, int x_layout, int64_t x_ld, const void* h,
+                       const void* bias, int bias_per_node, void* y, int y_layout, int64_t y_ld, void* workspace,
+                       size_t workspace_bytes, int B, int G, int F, int K, int activation, void* stream) {
+  return forward_impl(plan, x, x_layout, x_ld, h, bias, bias_per_node, y, y_layout, y_ld, workspace, workspace_bytes, B, G,
+                      F, K, activation, stream);
 }
 
 int b200gf_backward(const b200gf_plan* plan, const void* dy, int dy_layout, int64_t dy_ld, const void* x,

@@ -126,7 +126,8 @@ tap_contract_kernel(TermList terms, int T_terms, const T* __restrict__ W, const 
       if (q >= Q) continue;
       T val = acc[i][j];
       if (bias) val += bias_per_node ? bias[(int64_t)q * n_rows + n] : bias[q];
-      if (accumulate) val += o[q];
+      if (accumulate & 1) val += o[q];
+      if (accumulate & 2) val = val > T(0) ? val : T(0);   // fused ReLU epilogue (last launch of the chain only)
       o[q] = val;
     }
   }
@@ -134,7 +135,7 @@ tap_contract_kernel(TermList terms, int T_terms, const T* __restrict__ W, const 
 
 int launch_tap_contract(int dtype, int64_t n_rows, int B, int P, int Q, int T, const void* const* zs,
                         const int64_t* z_ld, const void* W, const void* bias, int bias_per_node, void* out,
-                        int64_t out_ld, int accumulate, cudaStream_t st) {
+                        int64_t out_ld, int accumulate, cudaStream_t st, int act) {
   if (n_rows < 0 || B <= 0 || P <= 0 || Q <= 0 || T <= 0 || !zs || !z_ld || !W || !out) return B200GF_EINVAL;
   if (out_ld < (int64_t)B * Q) return B200GF_EINVAL;
   if (n_rows == 0) return B200GF_OK;
@@ -151,7 +152,7 @@ int launch_tap_contract(int dtype, int64_t n_rows, int B, int P, int Q, int T, c
     }
     const void* Wt = (const char*)W + (size_t)t0 * P * Q * es;
     const void* bb = t0 == 0 ? bias : nullptr;
-    const int acc = (t0 == 0) ? accumulate : 1;
+    const int acc = ((t0 == 0) ? (accumulate ? 1 : 0) : 1) | ((act && t0 + TermList::MAX_TERMS >= T) ? 2 : 0);
     if (dtype == B200GF_F32)
       tap_contract_kernel<float><<<grid, 256, 0, st>>>(tl, tn, (const float*)Wt, (const float*)bb, bias_per_node,
                                                        (float*)out, out_ld, n_rows, B, P, Q, acc);

@@ -43,6 +43,7 @@ struct Params {
   int num_tiles;
   int stages;
   int bias_per_node;
+  int relu;          // epilogue activation: out = max(out, 0)  (fused GraphFilter -> ReLU layer, architectures.py:287)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -253,6 +254,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_contract_kernel(const __grid_co
                 o.z += __ldg(prm.bias + q + 2); o.w += __ldg(prm.bias + q + 3);
               }
             }
+            if (prm.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
             *reinterpret_cast<float4*>(orow + c0 + j) = o;
           }
         }
@@ -382,7 +384,7 @@ int launch_split_w(const void* W, void* whi_wlo, int T, int P, int Q, cudaStream
 // whi_wlo: device [2][T][Q][P] (hi then lo), K-major; everything else as launch_tap_contract
 int launch_tc_contract(int sm_count, int64_t n_rows, int B, int P, int Q, int T, const void* const* zs,
                        const void* whi_wlo, const void* bias, int bias_per_node, void* out, int64_t out_ld,
-                       cudaStream_t st) {
+                       cudaStream_t st, int act) {
   using namespace tc;
   EncodeTiledFn encode = get_encode();
   if (!encode) return B200GF_EUNSUPPORTED;
@@ -422,6 +424,7 @@ int launch_tc_contract(int sm_count, int64_t n_rows, int B, int P, int Q, int T,
   prm.num_tiles = (int)((R + BM - 1) / BM);
   prm.stages = stages_for(Q);
   prm.bias_per_node = bias_per_node;
+  prm.relu = act;
   const int stage_bytes = 2 * A_BYTES + 2 * Q * BK * 4;
   const size_t smem = (size_t)prm.stages * stage_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
   CUDA_TRY(cudaFuncSetAttribute(tc_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -89,7 +89,7 @@ class _LSIGFFunction(torch.autograd.Function):
     """y = LSIGF(h, S, x, b) with S fixed inside `plan` (graphML.py:83-176)."""
 
     @staticmethod
-    def forward(ctx, h, x, b, plan):
+    def forward(ctx, h, x, b, plan, act=0):
         lib = _cabi.load()
         F_, E, K, G = h.shape
         B, _, N = x.shape
@@ -106,28 +106,41 @@ class _LSIGFFunction(torch.autograd.Function):
         ybuf = torch.empty((N, ldf), dtype=dt, device=x.device)
         ws_bytes = lib.b200gf_workspace_bytes(plan.handle, B, G, F_, K, _cabi.NODE_MAJOR, 0)
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=x.device)
-        rc = lib.b200gf_forward(plan.handle, xn.data_ptr(), _cabi.NODE_MAJOR, x_ld, hc.data_ptr(),
-                                None if bc is None else bc.data_ptr(), bias_per_node,
-                                ybuf.data_ptr(), _cabi.NODE_MAJOR, ldf, ws.data_ptr(), ws_bytes,
-                                B, G, F_, K, _stream())
+        rc = lib.b200gf_forward_act(plan.handle, xn.data_ptr(), _cabi.NODE_MAJOR, x_ld, hc.data_ptr(),
+                                    None if bc is None else bc.data_ptr(), bias_per_node,
+                                    ybuf.data_ptr(), _cabi.NODE_MAJOR, ldf, ws.data_ptr(), ws_bytes,
+                                    B, G, F_, K, int(act), _stream())
         _cabi.check(rc)
+        ctx.act = int(act)
+        ctx.ldf = ldf
         ctx.plan = plan
         ctx.x_ld = x_ld
         ctx.bias_per_node = bias_per_node
         ctx.has_bias = b is not None
         ctx.bias_shape = None if b is None else tuple(b.shape)
         ctx.dims = (B, G, F_, K, E, N)
-        ctx.save_for_backward(hc, xn)
+        if act:
+            ctx.save_for_backward(hc, xn, ybuf)      # the fused ReLU's backward needs only the layer output (y > 0)
+        else:
+            ctx.save_for_backward(hc, xn)
         return _as_bcn_view(ybuf, B, F_, N)
 
     @staticmethod
     def backward(ctx, dy):
         lib = _cabi.load()
-        hc, xn = ctx.saved_tensors
+        if ctx.act:
+            hc, xn, ybuf = ctx.saved_tensors
+        else:
+            hc, xn = ctx.saved_tensors
         B, G, F_, K, E, N = ctx.dims
         plan = ctx.plan
         dt = hc.dtype
         dyn, dy_ld = to_node_major(dy)
+        if ctx.act:                                   # dy_pre = dy * (y > 0), one pass, node-major
+            masked = torch.empty((N, ctx.ldf), dtype=dt, device=dy.device)
+            _cabi.check(lib.b200gf_relu_backward(_ENUM[dt], ybuf.data_ptr(), ctx.ldf, dyn.data_ptr(), dy_ld,
+                                                 masked.data_ptr(), ctx.ldf, N, B * F_, _stream()))
+            dyn, dy_ld = masked, ctx.ldf
         need_dh, need_dx, need_db = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         dh = torch.empty_like(hc)
         ldc = padded_ld(B * G, dt)
@@ -153,11 +166,12 @@ class _LSIGFFunction(torch.autograd.Function):
                 dx = torch.empty((B, G, N), dtype=dt, device=dy.device)
                 _cabi.check(lib.b200gf_to_feature_major(_ENUM[dt], dxbuf.data_ptr(), ldc, dx.data_ptr(), N, B * G,
                                                         _stream()))
-        return (dh if need_dh else None), dx, db, None
+        return (dh if need_dh else None), dx, db, None, None
 
 
-def LSIGF(h, S, x, b=None):
+def LSIGF(h, S, x, b=None, activation=None):
     """LSIGF(filter_taps, GSO, input, bias=None): linear shift-invariant graph filter, then bias.
+    `activation="relu"` (extension) fuses the layer's ReLU into the contraction epilogue.
 
     Same contract as the reference (alegnn/utils/graphML.py:83-176):
         h [F, E, K, G]; S [E, N, N] (dense tensor, or SparseGSO / Plan); x [B, G, N]; b [F, 1] or [F, N] or None
@@ -185,10 +199,14 @@ def LSIGF(h, S, x, b=None):
                                "[1, F, N]; got %s" % (tuple(b.shape),))
         if b.shape[0] == 1 and F_ > 1:
             b = b.expand(F_, b.shape[1])
-    return _dispatch(h, S, x, b)
+    if activation is None:
+        return _dispatch(h, S, x, b)
+    if activation != "relu":
+        raise ValueError("b200gf: fused activation must be None or 'relu', got %r" % (activation,))
+    return _dispatch(h, S, x, b, 1)
 
 
-def _dispatch_cuda(h, S, x, b):
+def _dispatch_cuda(h, S, x, b, act=0):
     """Device part of LSIGF: loud checks (there is no CPU path), plan lookup, the autograd function over the C ABI.
     `_dispatch` is the single hook the CPU tests replace with the oracle to exercise the argument handling above."""
     if x.device.type != "cuda":
@@ -201,7 +219,7 @@ def _dispatch_cuda(h, S, x, b):
     plan = plan_for(S, x.device)
     if plan.device != x.device and not (plan.device.index == (x.device.index or 0)):
         raise RuntimeError("b200gf: GSO plan lives on %s but x is on %s" % (plan.device, x.device))
-    return _LSIGFFunction.apply(h, x, b, plan)
+    return _LSIGFFunction.apply(h, x, b, plan, act)
 
 
 _dispatch = _dispatch_cuda
@@ -222,6 +240,7 @@ class GraphFilter(nn.Module):
         self.K = K
         self.E = E
         self.S = None
+        self.fused_activation = None                 # "relu" after fuse_layers(): the next module became nn.Identity
         self.weight = nn.parameter.Parameter(torch.Tensor(F, E, K, G))
         if bias:
             self.bias = nn.parameter.Parameter(torch.Tensor(F, 1))
@@ -253,7 +272,7 @@ class GraphFilter(nn.Module):
         Nin = x.shape[2]
         if Nin < self.N:                            # zero-pad the node axis, graphML.py:2131-2135
             x = torch.cat((x, torch.zeros(B, F, self.N - Nin, dtype=x.dtype, device=x.device)), dim=2)
-        u = LSIGF(self.weight, self.S, x, self.bias)  # plan lookup is cached per (tensor, version, device)
+        u = LSIGF(self.weight, self.S, x, self.bias, activation=self.fused_activation)  # plan lookup is cached
         if Nin < self.N:                            # keep the first Nin nodes, graphML.py:2142-2143
             u = u[:, :, :Nin]
         return u
@@ -266,6 +285,29 @@ class GraphFilter(nn.Module):
         else:
             reprString += "no GSO stored"
         return reprString
+
+
+def fuse_layers(model):
+    """Fuse `GraphFilter -> nn.ReLU -> (NoPool | MaxPoolLocal)` triples inside every nn.Sequential of `model` (the
+    reference builds its graph-filtering layers exactly like that, alegnn/modules/architectures.py:274-296):
+    the ReLU moves into the filter's contraction epilogue (the nn.ReLU module is replaced by nn.Identity, so the
+    Sequential keeps its indices and the checkpoint keys `GFL.<3l>.weight/bias` are unchanged) and a reference
+    MaxPoolLocal is swapped for this package's CUDA gather on the node-major output.  NoPool is an identity already.
+    Returns the number of fused layers."""
+    from . import pooling
+    fused = 0
+    for seq in [m for m in model.modules() if isinstance(m, nn.Sequential)]:
+        mods = list(seq._modules.items())
+        for i, (name, m) in enumerate(mods):
+            if isinstance(m, GraphFilter) and i + 1 < len(mods) and type(mods[i + 1][1]) is nn.ReLU:
+                m.fused_activation = "relu"
+                seq._modules[mods[i + 1][0]] = nn.Identity()
+                fused += 1
+                if i + 2 < len(mods):
+                    pname, pm = mods[i + 2]
+                    if type(pm).__name__ == "MaxPoolLocal" and not isinstance(pm, pooling.MaxPoolLocal):
+                        seq._modules[pname] = pooling.MaxPoolLocal.from_reference(pm)
+    return fused
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -104,6 +104,31 @@ int b200gf_forward(const b200gf_plan* plan,
                    void* workspace, size_t workspace_bytes,
                    int B, int G, int F, int K, void* stream);
 
+/* The same with the layer's activation fused into the contraction epilogue: the reference's
+ * selection architectures apply nn.ReLU right after every GraphFilter (alegnn/modules/architectures.py:274-296).
+ * activation: B200GF_ACT_NONE or B200GF_ACT_RELU (y = max(LSIGF(...), 0)); no extra pass over y. */
+enum { B200GF_ACT_NONE = 0, B200GF_ACT_RELU = 1 };
+int b200gf_forward_act(const b200gf_plan* plan,
+                       const void* x, int x_layout, int64_t x_ld,
+                       const void* h, const void* bias, int bias_per_node,
+                       void* y, int y_layout, int64_t y_ld,
+                       void* workspace, size_t workspace_bytes,
+                       int B, int G, int F, int K, int activation, void* stream);
+
+/* Backward of the fused ReLU from the layer OUTPUT alone: out = dy where y > 0, else 0 (node-major [n_rows, ld]). */
+int b200gf_relu_backward(int dtype, const void* y, int64_t y_ld, const void* dy, int64_t dy_ld,
+                         void* out, int64_t out_ld, int64_t n_rows, int C, void* stream);
+
+/* MaxPoolLocal (alegnn/utils/graphML.py:1968-2019) on node-major data: out[i, c] = max_j x[nb[i, j], c], i < n_out,
+ * nb = the layer's neighbourhood matrix [n_out, max_nb] (int32, rows padded with a member of the list, as
+ * graphTools.computeNeighborhood 'matrix' pads them).  argmax (optional, int32 [n_out, C]) receives the winning node of
+ * every output element; the backward zeroes dx [n_in, dx_ld] and adds dy[i, c] to dx[argmax[i, c], c]. */
+int b200gf_maxpool_forward(int dtype, const void* x, int64_t x_ld, int64_t n_in, int C,
+                           const int32_t* nb, int64_t n_out, int max_nb,
+                           void* out, int64_t out_ld, int32_t* argmax, void* stream);
+int b200gf_maxpool_backward(int dtype, const void* dy, int64_t dy_ld, const int32_t* argmax, int64_t n_out, int C,
+                            void* dx, int64_t dx_ld, int64_t n_in, void* stream);
+
 /* LSIGF backward (autograd of the above)
  *   V_{e,0} = dy,  V_{e,k} = V_{e,k-1} S_e^T              (K-1 hops with the backward operator)
  *   dx      = sum_{e,k,f} h[f,e,k,g] V_{e,k}[.,f,.]        (NULL to skip)

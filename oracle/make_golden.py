@@ -9,6 +9,9 @@ output of the reference's own code:
                       non-symmetric GSOs), plus the reference's own fp32 forward (its noise floor).
   graphfilter_cases.npz – `alegnn.utils.graphML.GraphFilter` (graphML.py:2036-2155) incl. the N_in < N
                       zero-pad / truncate path (:2131-2143).
+  layer_cases.npz   – the layer the selection architectures stack (architectures.py:274-296):
+                      `GraphFilter` -> `nn.ReLU` -> `MaxPoolLocal` (graphML.py:1968-2019), forward + all gradients and
+                      the reference's neighbourhood matrix.
   selectiongnn_cfg1.npz – BASELINE.json configs[0]: reference `Graph('SBM',50,...)`, `S = W/lambda_max`,
                       `SelectionGNN([1,32],[5],...)` (architectures.py:166-180) forward + backward in fp64;
                       state_dict, input batch, output and the parameter gradients.
@@ -129,6 +132,40 @@ def gen_selectiongnn_cfg1(gml):
         torch.set_default_dtype(torch.float32)
     np.savez_compressed(os.path.join(OUT, "selectiongnn_cfg1.npz"), **out)
     print("selectiongnn_cfg1.npz: keys", sorted(out.keys()))
+
+
+# GraphFilter -> nn.ReLU -> MaxPoolLocal, the layer of the selection architectures (architectures.py:274-296)
+LAYER_CASES = [
+    # (seed, N, Nout, B, G, F, K, E, hops)
+    (301, 30, 30, 2, 3, 5, 3, 1, 1),
+    (302, 40, 17, 3, 4, 6, 4, 2, 2),
+    (303, 25, 9, 1, 2, 8, 2, 1, 3),
+]
+
+
+def gen_layer(gml):
+    import torch.nn as nn
+    out = {}
+    for (seed, N, Nout, B, G, F, K, E, hops) in LAYER_CASES:
+        rng = np.random.default_rng(seed)
+        S = np.abs(orc.random_sparse_gso(rng, N, 4, E, symmetric=True))
+        torch.manual_seed(seed)
+        gf = gml.GraphFilter(G, F, K, E, True).double()
+        gf.addGSO(torch.tensor(S))
+        pool = gml.MaxPoolLocal(N, Nout, hops)
+        pool.addGSO(torch.tensor(S))
+        net = nn.Sequential(gf, nn.ReLU(), pool)
+        x = torch.tensor(rng.standard_normal((B, G, N)), requires_grad=True)
+        y = net(x)
+        dy = torch.tensor(rng.standard_normal(tuple(y.shape)))
+        y.backward(dy)
+        c = "l%d" % seed
+        out.update({c + "_S": S, c + "_x": x.detach().numpy(), c + "_dy": dy.numpy(), c + "_y": y.detach().numpy(),
+                    c + "_weight": gf.weight.detach().numpy(), c + "_bias": gf.bias.detach().numpy(),
+                    c + "_dx": x.grad.numpy(), c + "_dweight": gf.weight.grad.numpy(), c + "_dbias": gf.bias.grad.numpy(),
+                    c + "_neighborhood": pool.neighborhood.numpy(), c + "_meta": np.array([N, Nout, B, G, F, K, E, hops])})
+    np.savez_compressed(os.path.join(OUT, "layer_cases.npz"), **out)
+    print("layer_cases.npz:", len(LAYER_CASES), "cases")
 
 
 def gen_evgf(gml):
@@ -266,6 +303,6 @@ if __name__ == "__main__":
     gml = ref_import.import_reference()
     only = set(sys.argv[1:])                               # e.g. `python oracle/make_golden.py grnn`
     for name, gen in (("lsigf", gen_lsigf), ("graphfilter", gen_graphfilter), ("selectiongnn_cfg1", gen_selectiongnn_cfg1),
-                      ("evgf", gen_evgf), ("grnn", gen_grnn), ("lsigf_db", gen_lsigf_db)):
+                      ("evgf", gen_evgf), ("grnn", gen_grnn), ("lsigf_db", gen_lsigf_db), ("layer", gen_layer)):
         if not only or name in only:
             gen(gml)
