@@ -102,6 +102,13 @@ int launch_tc_contract(int sm_count, int64_t n_rows, int B, int P, int Q, int T,
                        const void* whi_wlo, const void* bias, int bias_per_node, void* out, int64_t out_ld,
                        cudaStream_t st, int act = 0);
 
+// FP64 contraction on DMMA (mma.sync.m8n8k4.f64), dmma_contract.cu; W is the plain [T][P][Q] packing
+bool dmma_contract_eligible(int dtype, int64_t n_rows, int B, int P, int Q, int T, const void* const* zs,
+                            const int64_t* z_ld, const void* out, int64_t out_ld, int accumulate);
+int launch_dmma_contract(int sm_count, int64_t n_rows, int B, int P, int Q, int T, const void* const* zs,
+                         const int64_t* z_ld, const void* W, const void* bias, int bias_per_node, void* out,
+                         int64_t out_ld, cudaStream_t st, int act);
+
 int launch_pack_taps(int dtype, const void* h, void* W, int F, int E, int K, int G, int transpose_taps,
                      cudaStream_t st);
 int launch_to_node_major(int dtype, const void* src, void* dst, int64_t dst_ld, int64_t N, int C,

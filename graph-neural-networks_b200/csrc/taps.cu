@@ -139,6 +139,13 @@ int launch_tap_contract(int dtype, int64_t n_rows, int B, int P, int Q, int T, c
   if (n_rows < 0 || B <= 0 || P <= 0 || Q <= 0 || T <= 0 || !zs || !z_ld || !W || !out) return B200GF_EINVAL;
   if (out_ld < (int64_t)B * Q) return B200GF_EINVAL;
   if (n_rows == 0) return B200GF_OK;
+  if (dmma_contract_eligible(dtype, n_rows, B, P, Q, T, zs, z_ld, out, out_ld, accumulate)) {
+    for (int t = 0; t < T; ++t)
+      if (!zs[t] || z_ld[t] < (int64_t)B * P) return B200GF_EINVAL;
+    int sms = 148, dev = 0;                      // FP64: the DMMA kernel (dmma_contract.cu)
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return launch_dmma_contract(sms, n_rows, B, P, Q, T, zs, z_ld, W, bias, bias_per_node, out, out_ld, st, act);
+  }
   const int64_t R = n_rows * B;
   dim3 grid((unsigned)((R + TC_BM - 1) / TC_BM), (unsigned)((Q + TC_BN - 1) / TC_BN));
   const size_t es = dtype_size(dtype);

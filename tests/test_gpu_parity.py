@@ -115,6 +115,7 @@ SPARSE_CASES = [
     (2000, 40, 2, 1, 32, 5, 1, "F1"),       # G = 1 first layer (cfg1 shape), rows longer than one 32-entry batch
     (1500, 5, 1, 6, 4, 1, 1, None),         # K = 1
     (2048, 10, 2, 32, 16, 3, 4, None),      # cfg4 shape (E = 4, K = 3)
+    (2200, 9, 2, 64, 32, 4, 2, "FN"),       # F = 32: 32-column block of the FP64 DMMA contraction, per-node bias
 ]
 
 

@@ -198,6 +198,14 @@ int main(int argc, char** argv) {
   const double peak = argc > 5 ? atof(argv[5]) : 6566.7;
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   printf("device %s  SMs %d  N=%lld deg=%d C=%d\n", prop.name, prop.multiProcessorCount, (long long)N, deg, C);
+  printf("L2 %d MB, persistingL2CacheMaxSize %d MB, accessPolicyMaxWindowSize %d MB\n", prop.l2CacheSize >> 20,
+         prop.persistingL2CacheMaxSize >> 20, prop.accessPolicyMaxWindowSize >> 20);
+  if (getenv("SWEEP_PERSIST_MB")) {   // L2 set-aside for evict_last ("persisting") lines; the default is 0
+    size_t want = (size_t)atoi(getenv("SWEEP_PERSIST_MB")) << 20, got = 0;
+    cudaError_t e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+    cudaDeviceGetLimit(&got, cudaLimitPersistingL2CacheSize);
+    printf("cudaLimitPersistingL2CacheSize: asked %zu MB -> %s, now %zu MB\n", want >> 20, cudaGetErrorString(e), got >> 20);
+  }
 
   std::mt19937_64 rng(12345);
   std::poisson_distribution<int> pd(deg);
@@ -245,6 +253,7 @@ int main(int argc, char** argv) {
   std::vector<V> vs;
 #define ADD(NAME, ...) vs.push_back(V{NAME, [&](bool ref) { return run<__VA_ARGS__>(P, NAME, reps, peak, 0, ref, 1.0f); }, {0, 0, 0}})
   //                                   L   U  THR MINB HINT PF SH
+#define ADDW(NAME, FRAC, ...) vs.push_back(V{NAME, [&](bool) { return run_v2w<__VA_ARGS__>(P, NAME, reps, peak, FRAC); }, {0, 0, 0}})
 #define ADDMR(NAME, ...) vs.push_back(V{NAME, [&](bool) { return run_mr<__VA_ARGS__>(P, NAME, reps, peak); }, {0, 0, 0}})
   //                                  L  GS  U MINB HINT
   if (C <= 8) {           // feature-sharded multi-GPU slices: 32-byte rows
@@ -270,8 +279,34 @@ int main(int argc, char** argv) {
     ADDMR("mrow L8 GS16 U2 EL mb8",    8, 16, 2, 8, 3);
     ADDMR("mrow L8 GS32 U4 EL mb6",    8, 32, 4, 6, 3);
     ADDMR("mrow L8 GS16 U2 ldg mb6",   8, 16, 2, 6, 0);
+  } else if (C <= 64 && getenv("SWEEP_R2") && atoi(getenv("SWEEP_R2")) == 4) {
+    // column-split passes with the wide-lane kernel: the gathered slab per pass shrinks towards the L2 (2 x 32 columns:
+    // 128 MB, 4 x 16 columns: 64 MB at N = 1M) at the price of re-reading col/val once per pass
+    ADD("r1 shipped (EL noPF mb6)",    16, 4, 256, 6, 3, false);
+    ADDW("w 1pass L8 U4 mb4 EL",   1.0f,  8, 4, 256, 4, 3);
+    ADDW("w 2pass L4 U4 mb4 EL",   1.0f,  4, 4, 256, 4, 3);
+    ADDW("w 2pass L4 U2 mb6 EL",   1.0f,  4, 2, 256, 6, 3);
+    ADDW("w 2pass L4 U2 mb8 EL",   1.0f,  4, 2, 256, 8, 3);
+    ADDW("w 2pass L4 U4 mb4 noEL", 1.0f,  4, 4, 256, 4, 1);
+    ADDW("w 2pass L4 U1 mb8 EL",   1.0f,  4, 1, 256, 8, 3);
+    ADDW("w 4pass L2 U2 mb6 EL",   1.0f,  2, 2, 256, 6, 3);
+    ADDW("w 4pass L2 U1 mb8 EL",   1.0f,  2, 1, 256, 8, 3);
+    ADDW("w 4pass L2 U2 mb8 noEL", 1.0f,  2, 2, 256, 8, 1);
+  } else if (C <= 64 && getenv("SWEEP_R2") && atoi(getenv("SWEEP_R2")) == 3) {
+    ADD("r1 shipped (EL noPF mb6)",    16, 4, 256, 6, 3, false);
+    ADDW("w U4 mb4 EL all",        1.0f,  8, 4, 256, 4, 3);
+    ADDW("w U4 mb4 noEL",          1.0f,  8, 4, 256, 4, 1);
+    ADDW("w U4 mb4 ELf .15",       0.15f, 8, 4, 256, 4, 2);
+    ADDW("w U4 mb4 ELf .25",       0.25f, 8, 4, 256, 4, 2);
+    ADDW("w U4 mb4 ELf .35",       0.35f, 8, 4, 256, 4, 2);
+    ADDW("w U4 mb4 ELf .45",       0.45f, 8, 4, 256, 4, 2);
+    ADDW("w U4 mb4 ELf/EF .15",    0.15f, 8, 4, 256, 4, 6);
+    ADDW("w U4 mb4 ELf/EF .25",    0.25f, 8, 4, 256, 4, 6);
+    ADDW("w U4 mb4 ELf/EF .35",    0.35f, 8, 4, 256, 4, 6);
+    ADDW("w U4 mb4 ELf/EF .45",    0.45f, 8, 4, 256, 4, 6);
+    ADDW("w U4 mb4 ELf .25 st.cs", 0.25f, 8, 4, 256, 4, 2, 1);
+    ADDW("w U4 mb4 ELf .35 st.cs", 0.35f, 8, 4, 256, 4, 2, 1);
   } else if (C <= 64 && getenv("SWEEP_R2") && atoi(getenv("SWEEP_R2")) == 2) {
-#define ADDW(NAME, FRAC, ...) vs.push_back(V{NAME, [&](bool) { return run_v2w<__VA_ARGS__>(P, NAME, reps, peak, FRAC); }, {0, 0, 0}})
     ADD("r1 shipped (EL noPF mb6)",    16, 4, 256, 6, 3, false);
     //                                 L  U  THR MINB HINT SH
     ADDW("w U4 mb4 EL all",        1.0f,  8, 4, 256, 4, 3);
