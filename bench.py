@@ -20,8 +20,8 @@ A "step" is one LSIGF forward (alegnn/utils/graphML.py:83-176 semantics) over on
   cpu_baseline = the reference's dense torch.matmul algorithm (oracle/lsigf_oracle.py:lsigf_dense_torch, a port: the
            reference is Python, cannot be pip-installed offline — DESIGN.md §6 — and cannot travel to the GPU box) on this
            box's host cores, bounded sample, thread count pinned and printed.
-  configs = at N = 1 the other single-GPU configurations of BASELINE.json (cfg2, cfg3, cfg4) measured the same way in
-           the same run (fewer steps), each with its own parity number.
+  configs = at N = 1 the other single-GPU configurations of BASELINE.json (cfg2, cfg3, cfg4; cfg4ev = config 4 as the
+           reference's EdgeVariantGF layer) measured the same way in the same run (fewer steps), each with its own parity.
 Default workload = the configuration the north_star target is quoted on: ER N=1M, avgDeg=32, K=5, G=F=64, B=1, fp32.
 """
 import argparse
@@ -507,6 +507,77 @@ def single_gpu_workload(ctx, name, w, steps, warmup, full):
     return out, gso
 
 
+def edge_variant_workload(ctx, steps, warmup):
+    """BASELINE.json config 4 at its stated size as the reference's layer type: hybrid EdgeVariantGF (EdgeNet) on ER
+    N = 200k, avgDeg 16, tensor GSO E = 4, K = 3, G = F = 32, B = 32, M = 1024 selected nodes — gnn_b200.SparseEdgeVariantGF
+    (parameters per masked non-zero; the reference's dense weightEV would need 1.6e16 numbers).  One step = the layer's
+    forward = LSI part (LSIGF with the tensor GSO) + EV part (csrc/ev.cu chains on the compact node set)."""
+    import gnn_b200
+    from gnn_b200 import edgevariant as evm
+    import lsigf_oracle as orc
+    w = WORKLOADS["cfg4"]
+    dev, tdt, es = ctx.dev, ctx.tdt, ctx.es
+    E, K, G, F, B, N, M = w["E"], w["K"], w["G"], w["F"], w["B"], w["N"], 1024
+    gso = make_gso(w).astype(tdt)
+    torch.manual_seed(4)
+    layer = gnn_b200.SparseEdgeVariantGF(G, F, K, M, N, E, True).to(dev, tdt)
+    layer.addGSO(gso, device=dev)
+    st = layer._struct
+    nnz_m = [pe["nnz"] for pe in st.per_e]
+    n_diag = [int((pe["diag"] >= 0).sum()) for pe in st.per_e]
+    x = torch.randn(B, G, N, generator=torch.Generator().manual_seed(1)).to(dev, tdt)
+    ops_lsi = float(gso.nnz()) * (K - 1) * B * G
+    ops_ev = float(sum(F * G * B * (n * (K - 1) + d) for n, d in zip(nnz_m, n_diag)))
+    fwd = lambda: layer(x)                                   # noqa: E731
+    with torch.no_grad(), ClockSampler(ctx.local) as clk:
+        ms, launches = ctx.timed(fwd, steps, warmup)
+    xA = x.index_select(2, st.A)
+
+    def ev_only():
+        for e in range(E):
+            evm._chain(layer.weightEV[e], xA, st.per_e[e], st.NA, True)
+
+    with torch.no_grad():
+        ms_ev, launches_ev = ctx.timed(ev_only, steps, warmup)
+    # gather-model bytes of the EV part per forward: every step reads its weights once, one B-wide state row per
+    # non-zero and chain, and writes one state row per chain and node (the last step writes only Y)
+    by = 0.0
+    for n, d in zip(nnz_m, n_diag):
+        by += F * G * d * es + F * G * d * B * es + F * G * st.NA * B * es + F * st.NA * B * es                   # k = 0 (diagonal)
+        for k in range(1, K):
+            by += F * G * n * es + n * 4 + F * G * n * B * es + (F * G * st.NA * B * es if k < K - 1 else 0) + 2 * F * st.NA * B * es
+    out = {"workload": "hybrid EdgeVariantGF (EdgeNet) " + describe(w, ctx.args.dtype) + " M=%d" % M,
+           "ms_per_step": ms, "value": (ops_lsi + ops_ev) / (ms * 1e-3), "unit": "edge-feature-op/s",
+           "ops_per_step": {"lsi": ops_lsi, "edge_variant": ops_ev}, "gpu_launches": launches,
+           "edge_variant_part": {"ms": ms_ev, "compact_nodes": st.NA, "masked_nnz_per_e": nnz_m,
+                                 "parameters": int(sum(p.numel() for p in layer.weightEV)),
+                                 "value": ops_ev / (ms_ev * 1e-3), "gpu_launches": launches_ev,
+                                 "roofline": {"bound": "hbm", "kernel": "ev::step_kernel", "bytes_per_forward": by,
+                                              "achieved": by / (ms_ev * 1e-3) / 1e9, "peak": ctx.peak, "unit": "GB/s",
+                                              "frac": by / (ms_ev * 1e-3) / 1e9 / ctx.peak}},
+           "clocks": clk.summary()}
+    if not ctx.args.no_check:
+        # EV part of two output features against the fp64 scipy chains, LSI part against the LSIGF oracle is cfg4's own check
+        with torch.no_grad():
+            yA = None
+            for e in range(E):
+                ye = evm._chain(layer.weightEV[e], xA, st.per_e[e], st.NA, True)
+                yA = ye if yA is None else yA + ye
+            errs = []
+            xA_c = xA.double().cpu().numpy()
+            for f in (0, F - 1):
+                want = 0
+                for e in range(E):
+                    pe = st.per_e[e]
+                    want = want + orc.evgf_sparse_chains(pe["rowptr"].cpu().numpy(), pe["col"].cpu().numpy(),
+                                                         layer.weightEV[e][f].double().cpu().numpy(), xA_c, k0_identity=True)
+                got = yA[:, f, :].double().cpu().numpy()
+                errs.append(float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-300)))
+        out["parity_max_rel"] = max(errs)
+        out["parity_note"] = "EV part, output features 0 and F-1 on all %d compact nodes x %d samples vs fp64 scipy chains" % (st.NA, B)
+    return out
+
+
 def multi_gpu_selftest(ctx):
     """Forward AND backward of both shardings on a small graph against the fp64 oracle, over the same NCCL / NVLink ranks
     the bench uses (the partitioned backward and the fused kernels above 2 ranks had no hardware evidence)."""
@@ -775,6 +846,15 @@ def run_gpu_arm(args, w):
         line["configs"] = {}
     for name in extra:
         torch.cuda.empty_cache()
+        if name == "cfg4ev":
+            try:
+                r = edge_variant_workload(ctx, max(3, min(args.steps, 5)), 3)
+                line["configs"][name] = r
+                if r.get("parity_max_rel") is not None and not r["parity_max_rel"] < ctx.tol:
+                    bad.append("cfg4ev parity_max_rel %.3e" % r["parity_max_rel"])
+            except Exception as exc:
+                line["configs"][name] = {"error": repr(exc)[:300]}
+            continue
         try:
             r, _ = single_gpu_workload(ctx, name, WORKLOADS[name], max(3, min(args.steps, 10)), 3, full=False)
             rf = r.get("roofline") or {}
@@ -813,7 +893,7 @@ def main():
                     help="multi-GPU sharding (DESIGN.md §4): node rows (north_star), feature columns, or probe both and "
                          "time the faster one (default)")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"], help="arithmetic type (headline: f32)")
-    ap.add_argument("--configs", default="cfg2,cfg3,cfg4",
+    ap.add_argument("--configs", default="cfg2,cfg3,cfg4,cfg4ev",
                     help="N = 1: other BASELINE.json configurations measured in the same run ('' = none)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-size-cpu", action="store_true", help="reference arm: skip the full-size sparse CPU figure")

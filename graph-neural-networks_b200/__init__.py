@@ -7,7 +7,7 @@ from . import _cabi  # noqa: F401
 from .gso import SparseGSO, Plan, plan_for, clear_plan_cache  # noqa: F401
 from .graphML import LSIGF, GraphFilter, install, uninstall, fuse_layers, to_node_major, to_feature_major, node_major_ld, padded_ld  # noqa: F401
 
-from .edgevariant import EVGF, EdgeVariantGF  # noqa: F401,E402
+from .edgevariant import EVGF, EdgeVariantGF, SparseEdgeVariantGF  # noqa: F401,E402
 from .pooling import MaxPoolLocal  # noqa: F401,E402
 from .activations import MaxLocalActivation, MedianLocalActivation, NoActivation  # noqa: F401,E402
 from .recurrent import GatedGRNN, HiddenState, TimeGatedHiddenState, NodeGatedHiddenState  # noqa: F401,E402

@@ -54,9 +54,10 @@ _SIGNATURES = {
     "b200gf_symm_close": (c_int, [c_vp]),
     "b200gf_peer_signal": (c_int, [PP, c_int, c_int, c_vp, c_vp]),
     "b200gf_peer_wait": (c_int, [c_vp, c_int, c_vp, c_vp]),
-    "b200gf_ev_forward": (c_int, [c_int, c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "b200gf_ev_backward": (c_int, [c_int, c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp,
-                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "b200gf_ev_forward": (c_int, [c_int, c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_int,
+                                  c_vp, c_vp]),
+    "b200gf_ev_backward": (c_int, [c_int, c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64,
+                                   c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "b200gf_tap_contract":(c_int, [c_int, c_i64, c_int, c_int, c_int, c_int, PP, ctypes.POINTER(c_i64), c_vp, c_vp,
                                     c_int, c_vp, c_i64, c_int, c_vp, c_sz, c_vp]),
     "b200gf_tap_contract_scratch_bytes": (c_sz, [c_int, c_int, c_int]),

@@ -6,153 +6,196 @@
 // and sums u_k over k, g, e.  The reference stores every Phi^(k)_{feg} as a dense N x N matrix; only the entries on
 // the masked sparsity pattern of |S_e| + I are live (:2620-2663).  Here the live entries are stored per non-zero of
 // one CSR pattern (rowptr, col) over a COMPACT node set A of NA nodes (for the hybrid layer: the M selected nodes and
-// the nodes adjacent to them — every other row and column of Phi is identically zero), one call per edge feature e:
-//     w    [F, K, G, nnz]   Phi^(k) on the pattern (k = 0 included: its off-diagonal entries are simply zero)
-//     xA   [B, G, NA]       input restricted to A
-//     S    [F, G, B, NA]    sum_k u_k   (the caller sums over g and e and adds the bias)
-// chains c = (f*G + g)*B + b ; states u_k [c, NA] are kept for the backward pass.
+// the nodes adjacent to them — every other row and column of Phi is identically zero), one call per edge feature e.
+//
+// Round-2 layout: the BATCH index is innermost everywhere,
+//     w    [F, K, G, nnz]      Phi^(k) on the pattern
+//     xT   [G, NA, B]          input restricted to A
+//     U_k  [F*G, NA, B]        chain states u_k (kept for k < K-1: the weight gradient of step k+1 needs them)
+//     Y    [F, NA, B]          sum_g sum_k u_k   (the caller sums over e and adds the bias)
+// so that the B chains sharing one weight matrix Phi^(k)_{feg} sit in adjacent lanes: one weight / column index is read
+// once per warp and broadcast, every state access is a coalesced B*s-byte row (the r1 kernels had the node index
+// innermost: every lane read its own weights, states were gathered element-wise, and an extra [F,G,B,NA] running sum
+// was read-modified-written once per k).  The sum over g happens in registers (one thread owns (f, i, b) and loops
+// over g), so Y is written once per step.  `diag` (optional, int32 [NA]): position of the diagonal entry of row i in
+// the pattern, -1 if it is not live — the layer's k = 0 mask is "identity on the selected nodes" (:2653-2663), so its
+// first step is an element-wise product, not a sparse product; without `diag` (functional EVGF with arbitrary matrices)
+// k = 0 runs like every other step.
 #include "common.cuh"
 
 namespace b200gf {
 namespace ev {
 
-// u_k[c, i] = sum_{idx in row i} w_k[f, g, idx] * prev[col[idx]] ;  S (+)= u_k.   k = 0 reads x instead of u_{-1}
+// step k of every chain (f, g, b) for one edge feature
 template <typename T>
-__global__ void hop_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const T* __restrict__ w,
-                           const T* __restrict__ uprev, const T* __restrict__ xA, T* __restrict__ ucur, T* __restrict__ S,
-                           int64_t NA, int B, int G, int K, int k, int64_t nnz, int64_t total) {
+__global__ void __launch_bounds__(256)
+step_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ diag,
+            const T* __restrict__ w, const T* __restrict__ uprev, const T* __restrict__ xT, T* __restrict__ ucur,
+            T* __restrict__ Y, int64_t NA, int B, int G, int K, int k, int64_t nnz, int64_t total /* F*NA*B */) {
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t c = t / NA;
-    const int i = (int)(t - c * NA);
-    const int b = (int)(c % B);
-    const int64_t fg = c / B;
-    const int64_t f = fg / G;
-    const int g = (int)(fg - f * G);
-    const T* __restrict__ wk = w + ((f * K + k) * G + g) * nnz;
-    const T* __restrict__ up = k == 0 ? xA + ((int64_t)b * G + g) * NA : uprev + c * NA;
-    T acc = T(0);
-    for (int64_t idx = rowptr[i]; idx < rowptr[i + 1]; ++idx) acc = fma(wk[idx], up[col[idx]], acc);
-    ucur[t] = acc;
-    S[t] = k == 0 ? acc : S[t] + acc;
+    const int b = (int)(t % B);
+    const int64_t fi = t / B;
+    const int64_t i = fi % NA;
+    const int64_t f = fi / NA;
+    const int64_t beg = rowptr[i], end = rowptr[i + 1];
+    T ysum = T(0);
+    for (int g = 0; g < G; ++g) {
+      const T* __restrict__ wk = w + ((f * K + k) * G + g) * nnz;
+      const T* __restrict__ up = (k == 0 ? xT + (int64_t)g * NA * B : uprev + (f * G + g) * NA * B) + b;
+      T acc = T(0);
+      if (k == 0 && diag) {
+        const int32_t d = diag[i];
+        if (d >= 0) acc = wk[d] * up[i * B];
+      } else {
+        for (int64_t idx = beg; idx < end; ++idx) acc = fma(wk[idx], up[(int64_t)col[idx] * B], acc);
+      }
+      if (ucur) ucur[((f * G + g) * NA + i) * B + b] = acc;
+      ysum += acc;
+    }
+    Y[t] = k == 0 ? ysum : Y[t] + ysum;
   }
 }
 
-// lam_{K-1}[c, i] = dyA[b, f, i]
+// lam_{K-1}[(f,g), i, b] = dY[f, i, b]
 template <typename T>
-__global__ void adjoint_init_kernel(const T* __restrict__ dyA, T* __restrict__ lam, int64_t NA, int B, int G, int F,
-                                    int64_t total) {
+__global__ void adjoint_init_kernel(const T* __restrict__ dY, T* __restrict__ lam, int64_t NA, int B, int G, int64_t total) {
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t c = t / NA;
-    const int i = (int)(t - c * NA);
-    const int b = (int)(c % B);
-    const int64_t f = (c / B) / G;
-    lam[t] = dyA[((int64_t)b * F + f) * NA + i];
+    const int64_t ib = t % (NA * B);
+    const int64_t f = (t / (NA * B)) / G;
+    lam[t] = dY[f * NA * B + ib];
   }
 }
 
-// lam_{k-1}[c, j] = dyA[b, f, j] + sum_{it in rowT(j)} w_k[perm[it]] * lam_k[c, colT[it]]        (k >= 1)
+// lam_{k-1}[(f,g), j, b] = dY[f, j, b] + sum_{it in rowT(j)} w_k[perm[it]] * lam_k[(f,g), colT[it], b]        (k >= 1)
 template <typename T>
-__global__ void adjoint_hop_kernel(const int64_t* __restrict__ rowptrT, const int32_t* __restrict__ colT,
-                                   const int64_t* __restrict__ perm, const T* __restrict__ w, const T* __restrict__ dyA,
-                                   const T* __restrict__ lam_k, T* __restrict__ lam_km1, int64_t NA, int B, int G, int F,
-                                   int K, int k, int64_t nnz, int64_t total) {
+__global__ void __launch_bounds__(256)
+adjoint_step_kernel(const int64_t* __restrict__ rowptrT, const int32_t* __restrict__ colT, const int64_t* __restrict__ perm,
+                    const T* __restrict__ w, const T* __restrict__ dY, const T* __restrict__ lam_k, T* __restrict__ lam_km1,
+                    int64_t NA, int B, int G, int K, int k, int64_t nnz, int64_t total /* F*G*NA*B */) {
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t c = t / NA;
-    const int j = (int)(t - c * NA);
-    const int b = (int)(c % B);
-    const int64_t fg = c / B;
+    const int b = (int)(t % B);
+    const int64_t cj = t / B;
+    const int64_t j = cj % NA;
+    const int64_t fg = cj / NA;
     const int64_t f = fg / G;
     const int g = (int)(fg - f * G);
     const T* __restrict__ wk = w + ((f * K + k) * G + g) * nnz;
-    const T* __restrict__ lk = lam_k + c * NA;
-    T acc = dyA[((int64_t)b * F + f) * NA + j];
-    for (int64_t it = rowptrT[j]; it < rowptrT[j + 1]; ++it) acc = fma(wk[perm[it]], lk[colT[it]], acc);
+    const T* __restrict__ lk = lam_k + fg * NA * B + b;
+    T acc = dY[(f * NA + j) * B + b];
+    for (int64_t it = rowptrT[j]; it < rowptrT[j + 1]; ++it) acc = fma(wk[perm[it]], lk[(int64_t)colT[it] * B], acc);
     lam_km1[t] = acc;
   }
 }
 
-// dw_k[f, g, idx(i, j)] = sum_b lam_k[(fg, b), i] * prev[(fg, b), j]      prev = u_{k-1}, or x for k = 0
+// dw_k[(f,g), idx(i, j)] = sum_b lam_k[(f,g), i, b] * prev[(f,g), j, b]      prev = u_{k-1}, or x_g for k = 0
+// One warp per ((f,g), row i): lanes run over b (coalesced rows), the products are reduced with shuffles, lane (n % 32)
+// keeps the result of the row's n-th entry so that the row's gradients leave in one coalesced store.
 template <typename T>
-__global__ void wgrad_kernel(const int32_t* __restrict__ rowidx, const int32_t* __restrict__ col, const T* __restrict__ lam_k,
-                             const T* __restrict__ uprev, const T* __restrict__ xA, T* __restrict__ dw, int64_t NA, int B,
-                             int G, int K, int k, int64_t nnz, int64_t total /* F*G*nnz */) {
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t fg = t / nnz;
-    const int64_t idx = t - fg * nnz;
+__global__ void __launch_bounds__(256)
+wgrad_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ diag,
+             const T* __restrict__ lam_k, const T* __restrict__ uprev, const T* __restrict__ xT, T* __restrict__ dw,
+             int64_t NA, int B, int G, int K, int k, int64_t nnz, int64_t n_items /* F*G*NA */) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < n_items; item += n_warps) {
+    const int64_t i = item % NA;
+    const int64_t fg = item / NA;
     const int64_t f = fg / G;
     const int g = (int)(fg - f * G);
-    const int i = rowidx[idx], j = col[idx];
-    T acc = T(0);
-    for (int b = 0; b < B; ++b) {
-      const int64_t c = fg * B + b;
-      const T p = k == 0 ? xA[((int64_t)b * G + g) * NA + j] : uprev[c * NA + j];
-      acc = fma(lam_k[c * NA + i], p, acc);
+    const int64_t beg = rowptr[i], end = rowptr[i + 1];
+    const T* __restrict__ li = lam_k + (fg * NA + i) * B;
+    const T* __restrict__ pv = k == 0 ? xT + (int64_t)g * NA * B : uprev + fg * NA * B;
+    T* __restrict__ out = dw + ((f * K + k) * G + g) * nnz;
+    const int32_t dg = (k == 0 && diag) ? diag[i] : -2;          // -2: general step
+    T keep = T(0);
+    for (int64_t idx = beg; idx < end; ++idx) {
+      T part = T(0);
+      if (dg == -2 || idx == dg) {
+        const T* __restrict__ pj = pv + (int64_t)col[idx] * B;
+        for (int b = lane; b < B; b += 32) part = fma(li[b], pj[b], part);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+      }
+      const int n = (int)(idx - beg);
+      if ((n & 31) == lane) keep = part;
+      if ((n & 31) == 31 || idx == end - 1) {                    // flush up to 32 results, coalesced
+        const int64_t base = idx - (n & 31);
+        if (base + lane <= idx) out[base + lane] = keep;
+      }
     }
-    dw[((f * K + k) * G + g) * nnz + idx] = acc;
   }
 }
 
-// dxA[b, g, j] = sum_f sum_{it in rowT(j)} w_0[f, g, perm[it]] * lam_0[((f*G + g)*B + b), colT[it]]
+// dxT[g, j, b] = sum_f sum_{it in rowT(j)} w_0[f, g, perm[it]] * lam_0[(f,g), colT[it], b]
 template <typename T>
-__global__ void xgrad_kernel(const int64_t* __restrict__ rowptrT, const int32_t* __restrict__ colT,
-                             const int64_t* __restrict__ perm, const T* __restrict__ w, const T* __restrict__ lam0,
-                             T* __restrict__ dxA, int64_t NA, int B, int G, int F, int K, int64_t nnz,
-                             int64_t total /* B*G*NA */) {
+__global__ void __launch_bounds__(256)
+xgrad_kernel(const int64_t* __restrict__ rowptrT, const int32_t* __restrict__ colT, const int64_t* __restrict__ perm,
+             const int32_t* __restrict__ diag, const T* __restrict__ w, const T* __restrict__ lam0, T* __restrict__ dxT,
+             int64_t NA, int B, int G, int F, int K, int64_t nnz, int64_t total /* G*NA*B */) {
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t bg = t / NA;
-    const int j = (int)(t - bg * NA);
-    const int b = (int)(bg / G);
-    const int g = (int)(bg - (int64_t)b * G);
+    const int b = (int)(t % B);
+    const int64_t gj = t / B;
+    const int64_t j = gj % NA;
+    const int64_t g = gj / NA;
     T acc = T(0);
-    for (int f = 0; f < F; ++f) {
-      const T* __restrict__ w0 = w + (((int64_t)f * K + 0) * G + g) * nnz;
-      const T* __restrict__ l0 = lam0 + (((int64_t)f * G + g) * B + b) * NA;
-      for (int64_t it = rowptrT[j]; it < rowptrT[j + 1]; ++it) acc = fma(w0[perm[it]], l0[colT[it]], acc);
+    for (int64_t f = 0; f < F; ++f) {
+      const T* __restrict__ w0 = w + ((f * K + 0) * G + g) * nnz;
+      const T* __restrict__ l0 = lam0 + (f * G + g) * NA * B + b;
+      if (diag) {
+        const int32_t d = diag[j];
+        if (d >= 0) acc = fma(w0[d], l0[j * B], acc);
+      } else {
+        for (int64_t it = rowptrT[j]; it < rowptrT[j + 1]; ++it) acc = fma(w0[perm[it]], l0[(int64_t)colT[it] * B], acc);
+      }
     }
-    dxA[t] = acc;
+    dxT[t] = acc;
   }
 }
 
 inline int grid_for(int64_t total) { return (int)imin64((total + 255) / 256, 148 * 16); }
 
 template <typename T>
-int forward_t(int64_t NA, int B, int G, int F, int K, const int64_t* rowptr, const int32_t* col, int64_t nnz, const T* w,
-              const T* xA, T* states, T* S, cudaStream_t st) {
-  const int64_t total = (int64_t)F * G * B * NA;
+int forward_t(int64_t NA, int B, int G, int F, int K, const int64_t* rowptr, const int32_t* col, const int32_t* diag,
+              int64_t nnz, const T* w, const T* xT, T* states, int n_states, T* Y, cudaStream_t st) {
+  const int64_t total = (int64_t)F * NA * B;
+  const int64_t chain = (int64_t)F * G * NA * B;
   if (total == 0) return B200GF_OK;
   for (int k = 0; k < K; ++k) {
-    hop_kernel<T><<<grid_for(total), 256, 0, st>>>(rowptr, col, w, k > 0 ? states + (int64_t)(k - 1) * total : nullptr, xA,
-                                                   states + (int64_t)k * total, S, NA, B, G, K, k, nnz, total);
+    // states: n_states buffers of F*G*NA*B.  n_states >= K-1: u_k kept in buffer k (training); n_states == 2: ping-pong
+    // (inference); the last step's state is never needed and is not written.
+    const T* prev = k > 0 ? states + (int64_t)((k - 1) % n_states) * chain : nullptr;
+    T* cur = k < K - 1 ? states + (int64_t)(k % n_states) * chain : nullptr;
+    step_kernel<T><<<grid_for(total), 256, 0, st>>>(rowptr, col, diag, w, prev, xT, cur, Y, NA, B, G, K, k, nnz, total);
     LAUNCH_CHECK();
   }
   return B200GF_OK;
 }
 
 template <typename T>
-int backward_t(int64_t NA, int B, int G, int F, int K, const int32_t* rowidx, const int32_t* col, const int64_t* rowptrT,
-               const int32_t* colT, const int64_t* perm, int64_t nnz, const T* w, const T* xA, const T* states,
-               const T* dyA, T* lam /* 2 x [chains, NA] */, T* dw, T* dxA, cudaStream_t st) {
-  const int64_t total = (int64_t)F * G * B * NA;
-  if (total == 0) return B200GF_OK;
+int backward_t(int64_t NA, int B, int G, int F, int K, const int64_t* rowptr, const int32_t* col, const int64_t* rowptrT,
+               const int32_t* colT, const int64_t* perm, const int32_t* diag, int64_t nnz, const T* w, const T* xT,
+               const T* states, const T* dY, T* lam /* 2 x [F*G, NA, B] */, T* dw, T* dxT, cudaStream_t st) {
+  const int64_t chain = (int64_t)F * G * NA * B;
+  if (chain == 0) return B200GF_OK;
   T* cur = lam;
-  T* nxt = lam + total;
-  adjoint_init_kernel<T><<<grid_for(total), 256, 0, st>>>(dyA, cur, NA, B, G, F, total);
+  T* nxt = lam + chain;
+  adjoint_init_kernel<T><<<grid_for(chain), 256, 0, st>>>(dY, cur, NA, B, G, chain);
   LAUNCH_CHECK();
-  const int64_t tw = (int64_t)F * G * nnz;
+  const int64_t items = (int64_t)F * G * NA;
   for (int k = K - 1; k >= 0; --k) {
-    if (tw > 0) {
-      wgrad_kernel<T><<<grid_for(tw), 256, 0, st>>>(rowidx, col, cur, k > 0 ? states + (int64_t)(k - 1) * total : nullptr,
-                                                    xA, dw, NA, B, G, K, k, nnz, tw);
+    if (nnz > 0) {
+      const int blocks = (int)imin64((items + 7) / 8, 148 * 16);
+      wgrad_kernel<T><<<blocks, 256, 0, st>>>(rowptr, col, diag, cur, k > 0 ? states + (int64_t)(k - 1) * chain : nullptr, xT, dw,
+                                              NA, B, G, K, k, nnz, items);
       LAUNCH_CHECK();
     }
     if (k == 0) break;
-    adjoint_hop_kernel<T><<<grid_for(total), 256, 0, st>>>(rowptrT, colT, perm, w, dyA, cur, nxt, NA, B, G, F, K, k, nnz,
-                                                           total);
+    adjoint_step_kernel<T><<<grid_for(chain), 256, 0, st>>>(rowptrT, colT, perm, w, dY, cur, nxt, NA, B, G, K, k, nnz, chain);
     LAUNCH_CHECK();
     T* tmp = cur; cur = nxt; nxt = tmp;
   }
-  const int64_t tx = (int64_t)B * G * NA;
-  xgrad_kernel<T><<<grid_for(tx), 256, 0, st>>>(rowptrT, colT, perm, w, cur, dxA, NA, B, G, F, K, nnz, tx);
+  const int64_t tx = (int64_t)G * NA * B;
+  xgrad_kernel<T><<<grid_for(tx), 256, 0, st>>>(rowptrT, colT, perm, diag, w, cur, dxT, NA, B, G, F, K, nnz, tx);
   LAUNCH_CHECK();
   return B200GF_OK;
 }
@@ -163,35 +206,39 @@ int backward_t(int64_t NA, int B, int G, int F, int K, const int32_t* rowidx, co
 extern "C" {
 
 int b200gf_ev_forward(int dtype, int64_t NA, int B, int G, int F, int K, const int64_t* rowptr, const int32_t* col,
-                      int64_t nnz, const void* w, const void* xA, void* states, void* S, void* stream) {
+                      const int32_t* diag, int64_t nnz, const void* w, const void* xT, void* states, int n_states, void* Y,
+                      void* stream) {
   using namespace b200gf;
   if (NA < 0 || B <= 0 || G <= 0 || F <= 0 || K <= 0 || nnz < 0) return B200GF_EINVAL;
-  if (!rowptr || !col || !xA || !states || !S || (nnz > 0 && !w)) return B200GF_EINVAL;
+  if (!rowptr || !col || !xT || !Y || (nnz > 0 && !w)) return B200GF_EINVAL;
+  if (K > 1 && (!states || n_states < 1 || (n_states < K - 1 && n_states != 2))) return B200GF_EINVAL;
+  if (K > 2 && n_states == 1) return B200GF_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B200GF_F32)
-    return ev::forward_t<float>(NA, B, G, F, K, rowptr, col, nnz, (const float*)w, (const float*)xA, (float*)states,
-                                (float*)S, st);
+    return ev::forward_t<float>(NA, B, G, F, K, rowptr, col, diag, nnz, (const float*)w, (const float*)xT, (float*)states,
+                                n_states < 1 ? 1 : n_states, (float*)Y, st);
   if (dtype == B200GF_F64)
-    return ev::forward_t<double>(NA, B, G, F, K, rowptr, col, nnz, (const double*)w, (const double*)xA, (double*)states,
-                                 (double*)S, st);
+    return ev::forward_t<double>(NA, B, G, F, K, rowptr, col, diag, nnz, (const double*)w, (const double*)xT, (double*)states,
+                                 n_states < 1 ? 1 : n_states, (double*)Y, st);
   return B200GF_EUNSUPPORTED;
 }
 
-int b200gf_ev_backward(int dtype, int64_t NA, int B, int G, int F, int K, const int32_t* rowidx, const int32_t* col,
-                       const int64_t* rowptrT, const int32_t* colT, const int64_t* perm, int64_t nnz, const void* w,
-                       const void* xA, const void* states, const void* dyA, void* lam, void* dw, void* dxA, void* stream) {
+int b200gf_ev_backward(int dtype, int64_t NA, int B, int G, int F, int K, const int64_t* rowptr, const int32_t* col,
+                       const int64_t* rowptrT, const int32_t* colT, const int64_t* perm, const int32_t* diag, int64_t nnz,
+                       const void* w, const void* xT, const void* states, const void* dY, void* lam, void* dw, void* dxT,
+                       void* stream) {
   using namespace b200gf;
   if (NA < 0 || B <= 0 || G <= 0 || F <= 0 || K <= 0 || nnz < 0) return B200GF_EINVAL;
-  if (!rowidx || !col || !rowptrT || !colT || !perm || !xA || !states || !dyA || !lam || !dxA) return B200GF_EINVAL;
+  if (!rowptr || !col || !rowptrT || !colT || !perm || !xT || !dY || !lam || !dxT || (K > 1 && !states)) return B200GF_EINVAL;
   if (nnz > 0 && (!w || !dw)) return B200GF_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B200GF_F32)
-    return ev::backward_t<float>(NA, B, G, F, K, rowidx, col, rowptrT, colT, perm, nnz, (const float*)w, (const float*)xA,
-                                 (const float*)states, (const float*)dyA, (float*)lam, (float*)dw, (float*)dxA, st);
+    return ev::backward_t<float>(NA, B, G, F, K, rowptr, col, rowptrT, colT, perm, diag, nnz, (const float*)w, (const float*)xT,
+                                 (const float*)states, (const float*)dY, (float*)lam, (float*)dw, (float*)dxT, st);
   if (dtype == B200GF_F64)
-    return ev::backward_t<double>(NA, B, G, F, K, rowidx, col, rowptrT, colT, perm, nnz, (const double*)w,
-                                  (const double*)xA, (const double*)states, (const double*)dyA, (double*)lam, (double*)dw,
-                                  (double*)dxA, st);
+    return ev::backward_t<double>(NA, B, G, F, K, rowptr, col, rowptrT, colT, perm, diag, nnz, (const double*)w,
+                                  (const double*)xT, (const double*)states, (const double*)dY, (double*)lam, (double*)dw,
+                                  (double*)dxT, st);
   return B200GF_EUNSUPPORTED;
 }
 

@@ -240,20 +240,24 @@ size_t b200gf_tap_grad_scratch_bytes(int dtype, int64_t n_rows, int B, int P, in
  *   EVGF(S, x, b)   alegnn/utils/graphML.py:389-488,   EdgeVariantGF.forward  :2670-2698
  * One call per edge feature e, on a compact node set of NA nodes (the rows/columns of Phi that are not identically
  * zero).  Pattern: CSR (rowptr [NA+1], col [nnz]) shared by all (f, k, g).  w [F, K, G, nnz] = Phi^(k)_{f e g} on the
- * pattern (COLUMN convention u_k = Phi^(k) u_{k-1}, u_{-1} = x_g).  xA [B, G, NA].
- * forward : states [K, F*G*B, NA] (kept for backward), S [F, G, B, NA] = sum_k u_k (caller sums over g, e; adds bias)
- * backward: dyA [B, F, NA] -> dw [F, K, G, nnz], dxA [B, G, NA]; needs rowidx [nnz] (row of each non-zero), the
- *           transposed pattern (rowptrT, colT) with perm[it] = index of that entry in the forward pattern, and
- *           lam = scratch of 2 * F*G*B*NA elements.
+ * pattern (COLUMN convention u_k = Phi^(k) u_{k-1}, u_{-1} = x_g).  The batch index is innermost in every operand:
+ *   xT [G, NA, B] (input on the compact set), states [n_states][F*G, NA, B] (u_k), Y [F, NA, B] = sum_g sum_k u_k
+ *   (the caller sums over e and adds the bias).
+ * diag (optional, int32 [NA]): index of row i's diagonal entry in the pattern, or -1 — when given, step k = 0 is the
+ *   layer's "identity on the selected nodes" mask (graphML.py:2653-2663): u_0[i] = w_0[diag[i]] x[i]; NULL = k = 0 is
+ *   an ordinary sparse step (functional EVGF with arbitrary matrices).
+ * forward : n_states >= K-1 keeps u_0 .. u_{K-2} for the backward pass; n_states == 2 ping-pongs (inference).
+ * backward: dY [F, NA, B] -> dw [F, K, G, nnz], dxT [G, NA, B]; needs the transposed pattern (rowptrT, colT) with
+ *           perm[it] = index of that entry in the forward pattern, and lam = scratch of 2 * F*G*NA*B elements.
  * ---------------------------------------------------------------------------------------------- */
 int b200gf_ev_forward(int dtype, int64_t NA, int B, int G, int F, int K,
-                      const int64_t* rowptr, const int32_t* col, int64_t nnz,
-                      const void* w, const void* xA, void* states, void* S, void* stream);
+                      const int64_t* rowptr, const int32_t* col, const int32_t* diag, int64_t nnz,
+                      const void* w, const void* xT, void* states, int n_states, void* Y, void* stream);
 int b200gf_ev_backward(int dtype, int64_t NA, int B, int G, int F, int K,
-                       const int32_t* rowidx, const int32_t* col,
-                       const int64_t* rowptrT, const int32_t* colT, const int64_t* perm, int64_t nnz,
-                       const void* w, const void* xA, const void* states, const void* dyA,
-                       void* lam, void* dw, void* dxA, void* stream);
+                       const int64_t* rowptr, const int32_t* col,
+                       const int64_t* rowptrT, const int32_t* colT, const int64_t* perm, const int32_t* diag, int64_t nnz,
+                       const void* w, const void* xT, const void* states, const void* dY,
+                       void* lam, void* dw, void* dxT, void* stream);
 
 /* layout conversion between the reference's [C, N] (feature-major, C = B*G) and node-major [N, ld] */
 int b200gf_to_node_major(int dtype, const void* src_cn, void* dst_nc, int64_t dst_ld,

@@ -354,6 +354,30 @@ def edge_variant_gf_forward(weightEV, weightLSI, bias, S, M, x):
     return y
 
 
+def evgf_sparse_chains(rowptr, col, w, xA, k0_identity=False):
+    """EVGF (graphML.py:389-488) for ONE output feature f and one edge feature e on a compact node set, with the filter
+    matrices given per non-zero of a CSR pattern: w [K, G, nnz], xA [B, G, NA] -> sum_g sum_k u_k, [B, NA], where
+    u_0 = Phi^(0) x_g, u_k = Phi^(k) u_{k-1} (column convention, :464,:475).  k0_identity: Phi^(0) keeps only its
+    diagonal (the layer's k = 0 mask, :2653-2663).  fp64 scipy; what the full-size EdgeNet check (bench cfg4ev) runs."""
+    w = np.asarray(w, dtype=np.float64)
+    xA = np.asarray(xA, dtype=np.float64)
+    K, G, nnz = w.shape
+    B, _, NA = xA.shape
+    rowptr = np.asarray(rowptr, dtype=np.int64)
+    col = np.asarray(col, dtype=np.int64)
+    rows = np.repeat(np.arange(NA), np.diff(rowptr))
+    out = np.zeros((NA, B))
+    for g in range(G):
+        u = np.ascontiguousarray(xA[:, g, :].T)                      # [NA, B]
+        for k in range(K):
+            wk = w[k, g]
+            if k == 0 and k0_identity:
+                wk = np.where(rows == col, wk, 0.0)
+            u = sp.csr_matrix((wk, col, rowptr), shape=(NA, NA)) @ u
+            out += u
+    return out.T
+
+
 # --------------------------------------------------------------------------------------------
 # sparse torch CPU restatement: second timed CPU baseline (NOT reference code — the reference has no sparse path)
 # --------------------------------------------------------------------------------------------

@@ -100,7 +100,7 @@ def test_hybrid_edge_variant_at_scale():
     for e in range(E):
         pe = st.per_e[e]
         w = torch.randn(F, K, G, pe["nnz"], dtype=torch.float64, device="cuda") * 0.3
-        y = y + evm._EVChain.apply(w, xA, pe, st.NA)
+        y = y + evm._EVChain.apply(w, xA, pe, st.NA, False)
         rows, cols = pe["rowidx"].long(), pe["col"].long()
         for f in range(F):
             for g in range(G):
@@ -111,3 +111,124 @@ def test_hybrid_edge_variant_at_scale():
                     u = u @ Phi.t()
                     y_ref[:, f, :] += u
     assert _rel(y.cpu().numpy(), y_ref.cpu().numpy()) < 1e-11
+
+
+# ------------------------------------------------------------------------------------------------ sparse-parameter layer
+def _dense_chain(w, xA, pe, NA, k0_identity=False):
+    """torch stand-in for csrc/ev.cu (CPU leg only): scatter the per-non-zero weights into dense NA x NA matrices and run
+    the chains u_k = Phi^(k) u_{k-1} of graphML.py:455-478."""
+    F_, K, G, nnz = w.shape
+    rows, cols = pe["rowidx"].long(), pe["col"].long()
+    y = 0
+    for k_mask in [None]:
+        Phi = torch.zeros(F_, K, G, NA, NA, dtype=w.dtype)
+        wk = w
+        if k0_identity:
+            on = (rows == cols).to(w.dtype)
+            wk = torch.cat((w[:, :1] * on, w[:, 1:]), dim=1)
+        Phi[:, :, :, rows, cols] = wk
+        u = xA.permute(1, 2, 0)[None].expand(F_, G, NA, xA.shape[0])              # [F, G, NA, B]
+        for k in range(K):
+            u = torch.einsum("fgij,fgjb->fgib", Phi[:, k], u)
+            y = y + u.sum(1)
+    return y.permute(2, 0, 1)                                                       # [B, F, NA]
+
+
+def _sparse_layer_from_fixture(z, tag, dtype, device):
+    import gnn_b200
+    N, M, E, K, G, F, B, Nin = [int(v) for v in z[tag + "_meta"]]
+    layer = gnn_b200.SparseEdgeVariantGF(G, F, K, M, N, E, True).to(device, dtype)
+    S = torch.tensor(z[tag + "_S"], dtype=dtype, device=device)
+    layer.addGSO(S, device=device)
+    layer.load_dense_state(torch.tensor(z[tag + "_p_weightEV"], dtype=dtype),
+                           torch.tensor(z[tag + "_p_weightLSI"], dtype=dtype) if (tag + "_p_weightLSI") in z.files else None,
+                           torch.tensor(z[tag + "_p_bias"], dtype=dtype))
+    return layer, (N, M, E, K, G, F, B, Nin)
+
+
+def _check_sparse_layer(z, tag, layer, dims, dtype, device, tol):
+    N, M, E, K, G, F, B, Nin = dims
+    x = torch.tensor(z[tag + "_x"], dtype=dtype, device=device, requires_grad=True)
+    y = layer(x)
+    assert tuple(y.shape) == z[tag + "_y"].shape
+    y.backward(torch.tensor(z[tag + "_dy"], dtype=dtype, device=device))
+    assert _rel(y.detach().cpu().numpy(), z[tag + "_y"]) < tol
+    assert _rel(x.grad.cpu().numpy(), z[tag + "_dx"]) < tol
+    gEV = z[tag + "_g_weightEV"]                                                     # dense reference gradient
+    for e, (p, pe) in enumerate(zip(layer.weightEV, layer._struct.per_e)):
+        want = gEV[:, e].reshape(F, K, G, N * N)[..., pe["lin"].cpu().numpy()]
+        assert _rel(p.grad.cpu().numpy(), want) < tol, ("weightEV", e)
+        off = (pe["rowidx"] != pe["col"]).cpu().numpy()
+        assert np.all(p.grad.cpu().numpy()[:, 0][..., off] == 0)                     # k = 0 off-diagonal slots: no gradient
+    if layer.weightLSI is not None:
+        assert _rel(layer.weightLSI.grad.cpu().numpy(), z[tag + "_g_weightLSI"]) < tol
+    assert _rel(layer.bias.grad.cpu().numpy(), z[tag + "_g_bias"]) < tol
+    # everything the reference layer would have as a parameter is there: masked entries only
+    dense_live = (z[tag + "_g_weightEV"] != 0).sum()
+    assert sum(p.numel() for p in layer.weightEV) >= dense_live
+
+
+@pytest.mark.parametrize("tag", ["full", "hyb"])
+def test_sparse_edge_variant_layer_host_logic(z, tag, monkeypatch):
+    """SparseEdgeVariantGF (parameters per masked non-zero) reproduces the reference layer from its dense checkpoint:
+    output, dx, and the gradient of every live parameter.  CPU: dense torch chain / oracle LSIGF behind the two hooks."""
+    from gnn_b200 import edgevariant as evm, graphML
+    monkeypatch.setattr(evm, "_chain", _dense_chain)
+    monkeypatch.setattr(graphML, "_dispatch", lambda h, S, x, b, act=0: orc.lsigf_dense_torch(h, S, x, b))
+    layer, dims = _sparse_layer_from_fixture(z, tag, torch.float64, "cpu")
+    monkeypatch.setattr(evm, "_require_cuda", lambda x: None)                        # the product forward itself runs
+    _check_sparse_layer(z, tag, layer, dims, torch.float64, "cpu", 1e-11)
+    monkeypatch.undo()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):                       # product behaviour on CPU tensors
+        layer(torch.zeros(1, dims[4], dims[0], dtype=torch.float64))
+    # round trip to the reference's dense parameter
+    dense = layer.dense_weightEV().numpy()
+    mask = z[tag + "_g_weightEV"] != 0
+    assert np.allclose(dense[mask], z[tag + "_p_weightEV"][mask])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["full", "hyb"])
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-11), (torch.float32, 1e-4)])
+def test_sparse_edge_variant_layer_gpu(z, tag, dtype, tol):
+    layer, dims = _sparse_layer_from_fixture(z, tag, dtype, "cuda")
+    _check_sparse_layer(z, tag, layer, dims, dtype, "cuda", tol)
+
+
+@pytest.mark.gpu
+def test_sparse_edge_variant_cfg4_size():
+    """BASELINE.json config 4 at its stated size: N = 200k, E = 4, K = 3, G = F = 32, hybrid with M = 1024 selected nodes —
+    the reference layer would need 32*4*3*32*4e10 parameters.  Constructs, runs forward + backward, and checks the EV part
+    against an fp64 evaluation of the same chains on a sub-sample of (f, g) pairs."""
+    import gnn_b200
+    from gnn_b200 import graphs
+    N, M, E, K, G, F, B = 200_000, 1024, 4, 3, 32, 32, 8
+    gso = graphs.er_gso(N, 16, seed=4, E=E)
+    layer = gnn_b200.SparseEdgeVariantGF(G, F, K, M, N, E, True).to("cuda")
+    layer.addGSO(gso, device="cuda")
+    st = layer._struct
+    n_par = sum(p.numel() for p in layer.weightEV)
+    assert st.NA < N // 4 and 1e7 < n_par < 1e9
+    x = torch.randn(B, G, N, device="cuda", requires_grad=True)
+    y = layer(x)
+    y.square().mean().backward()
+    torch.cuda.synchronize()
+    assert tuple(y.shape) == (B, F, N) and torch.isfinite(y).all() and torch.isfinite(x.grad).all()
+    assert all(torch.isfinite(p.grad).all() for p in layer.weightEV)
+    # EV part alone (sparse fp64 chains for two (f, g) pairs, every e): Y_ev = layer(x) - LSI part - 2 bias
+    with torch.no_grad():
+        lsi = gnn_b200.LSIGF(layer.weightLSI, gso, x, layer.bias) + layer.bias
+        ev = (y - lsi).index_select(2, st.A).double()                               # [B, F, NA]
+        xA = x.detach().index_select(2, st.A).double()
+        for f in (0, F - 1):
+            want = torch.zeros(B, st.NA, dtype=torch.float64, device="cuda")
+            for e in range(E):
+                pe = st.per_e[e]
+                rows, cols = pe["rowidx"].long(), pe["col"].long()
+                for g in range(G):
+                    u = xA[:, g, :]
+                    for k in range(K):
+                        wk = layer.weightEV[e][f, k, g].double()
+                        u = torch.zeros_like(u).index_add_(1, rows, wk[None, :] * u[:, cols])
+                        want += u
+            assert _rel(ev[:, f].cpu().numpy(), want.cpu().numpy()) < 2e-3          # fp32 difference of two large terms
