@@ -292,10 +292,16 @@ class PartitionedLSIGF:
     In both, row block p covers global nodes [p*rows_per_rank, (p+1)*rows_per_rank) (the last block is zero-padded).
     """
 
-    def __init__(self, gso, mode="nodes", group=None, device=None, ops=None, fused=None, fence="flags", symm_backend="auto"):
+    def __init__(self, gso, mode="nodes", group=None, device=None, ops=None, fused=None, fence="flags", symm_backend="auto",
+                 multicast=False):
         assert mode in ("nodes", "features") and fence in ("flags", "nccl")
         self.mode = mode
-        self.symm_backend = symm_backend   # "auto": torch symmetric memory (multicast when available), else CUDA IPC; "ipc"; "torch"
+        self.symm_backend = symm_backend   # "auto": torch symmetric memory, else CUDA IPC; "ipc"; "torch"
+        # all-gather epilogue: one multimem.st through the NVSwitch multicast address instead of P peer stores.  Off by
+        # default: measured slower for this pattern (2 GPUs: 2.78 vs 2.61 ms/step) — a multicast store also returns to the
+        # issuing GPU through its NVLink ingress, so every GPU receives N*C*s per hop instead of (P-1)/P of it, and the
+        # all-gather is ingress-bound (profiles/README.md)
+        self.multicast = bool(multicast)
         self.fence = fence          # "flags": peer flags in symmetric memory (no NCCL at all); "nccl": 4-byte all-reduce
         # fused = hop kernels scatter their rows over NVLink themselves (no NCCL collective on the data path);
         # default: on whenever the real CUDA ops run under NCCL with <= 16 ranks
@@ -402,6 +408,9 @@ class PartitionedLSIGF:
             buf = (self.n_pad * ld * es + 255) // 256 * 256
             a = SymmetricArena(self.ops.lib, n_bufs * buf, self.group, self.device, prefer=self.symm_backend)
             a.buf_bytes = buf
+            if not self.multicast:
+                a.mc = 0
+                a.kind = a.kind.replace("+multicast", " (multicast available, peer stores used)")
             self._arenas[key] = a
         return a
 
