@@ -272,7 +272,10 @@ class GraphFilter(nn.Module):
         Nin = x.shape[2]
         if Nin < self.N:                            # zero-pad the node axis, graphML.py:2131-2135
             x = torch.cat((x, torch.zeros(B, F, self.N - Nin, dtype=x.dtype, device=x.device)), dim=2)
-        u = LSIGF(self.weight, self.S, x, self.bias, activation=self.fused_activation)  # plan lookup is cached
+        if self.fused_activation is None:           # the reference's call, argument for argument (graphML.py:2137)
+            u = LSIGF(self.weight, self.S, x, self.bias)  # plan lookup is cached per (tensor, version, device)
+        else:
+            u = LSIGF(self.weight, self.S, x, self.bias, activation=self.fused_activation)
         if Nin < self.N:                            # keep the first Nin nodes, graphML.py:2142-2143
             u = u[:, :, :Nin]
         return u

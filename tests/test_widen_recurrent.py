@@ -152,3 +152,43 @@ def test_gpu_recursion_on_sparse_gso_at_scale():
     for t in range(T):
         zt = torch.tanh(gnn_b200.LSIGF(a, gso, x[:, t].contiguous(), None) + gnn_b200.LSIGF(b, gso, zt.contiguous(), None))
         assert torch.allclose(z[:, t], zt, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["HiddenState", "NodeGatedHiddenState"])
+def test_graphed_grnn_matches_eager(kind):
+    """the whole T-step recursion (one fused hop chain + contraction + gate + tanh per step) captured in
+    ONE CUDA graph replays bit-identically to the eager layer, on new input values, and is reported with its timing."""
+    import time
+    import gnn_b200
+    from gnn_b200 import recurrent as rec
+    from gnn_b200.graphs import er_gso
+    N, B, T, F, H, K = 400, 8, 40, 4, 16, 4
+    gso = er_gso(N, 8, seed=11, dtype=torch.float32)
+    torch.manual_seed(0)
+    layer = getattr(rec, kind)(F, H, K).cuda()
+    layer.addGSO(gso)
+    g = torch.Generator().manual_seed(1)
+    x, z0 = torch.randn(B, T, F, N, generator=g).cuda(), torch.randn(B, H, N, generator=g).cuda()
+    run = gnn_b200.graphed(lambda a, b: layer(a, b)[0], x, z0)
+    x2, z02 = torch.randn(B, T, F, N, generator=g).cuda(), torch.randn(B, H, N, generator=g).cuda()
+    with torch.no_grad():
+        want = layer(x2, z02)[0]
+    got = run(x2, z02)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+
+    def clock(fn, reps=5):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps * 1e3
+
+    with torch.no_grad():
+        eager_ms = clock(lambda: layer(x2, z02))
+    graph_ms = clock(lambda: run(x2, z02))
+    print("GRNN %s N=%d B=%d T=%d H=%d K=%d: eager %.2f ms / sequence, one CUDA graph %.2f ms (%.1fx)" %
+          (kind, N, B, T, H, K, eager_ms, graph_ms, eager_ms / graph_ms))
+    assert graph_ms < eager_ms
