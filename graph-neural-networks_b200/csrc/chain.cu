@@ -12,6 +12,8 @@
 // hop at N = 1682, C = 2048).  1024 threads: warp per row, lanes = 8 neighbour groups x 4 lanes x 16 bytes, the row's
 // col/val arrive with one coalesced load issued one row ahead (software prefetch), partial sums of the 8 groups are
 // folded with shuffles.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200gf {
@@ -135,12 +137,24 @@ static int launch_t(const CsrDev& A, int64_t n_rows, const T* src, int64_t src_l
 
 }  // namespace chain
 
+static size_t chain_max_bytes() {
+  static const size_t v = [] {
+    const char* e = getenv("B200GF_CHAIN_MAX_BYTES");   // 0 disables the chain kernel (A/B timing in tests)
+    return e ? (size_t)atoll(e) : (size_t)2 << 20;
+  }();
+  return v;
+}
+
 // square operators only (the chain feeds its own output back); every operand 16-byte aligned with C a whole number of
 // 16-byte vectors; the two slab buffers must fit the 227 KB of shared memory
 bool hop_chain_eligible(int dtype, const CsrDev& A, int64_t n_rows, int64_t n_cols, const void* src, int64_t src_ld,
                         void* const* dst, int64_t dst_ld, int C, int n_hops) {
   if (n_rows != n_cols || n_rows <= 0 || n_hops < 2 || n_hops > chain::MAX_HOPS) return false;   // one hop: the plain kernel
   const size_t es = dtype_size(dtype);
+  // Used only where it wins: launch-latency-bound chains.  At BASELINE config 3 (N = 1682, C = 2048: 14 MB per hop source)
+  // the separate hop kernels are L2-bandwidth-bound at 24.6 us per hop and this kernel, with one 1024-thread CTA per SM
+  // and its index loads missing the (shared-memory-sized-down) L1, took 50 us per hop (profiles/r2_bench_er1m_1gpu_b.json).
+  if ((size_t)n_rows * (size_t)C * es > chain_max_bytes()) return false;
   const int VEC = (int)(16 / es);
   if ((size_t)2 * n_rows * 64 > (size_t)227 * 1024 - 1024) return false;
   if (C % VEC != 0 || src_ld % VEC != 0 || dst_ld % VEC != 0 || (reinterpret_cast<uintptr_t>(src) & 15)) return false;

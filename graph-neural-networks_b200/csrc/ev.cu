@@ -26,33 +26,86 @@
 namespace b200gf {
 namespace ev {
 
-// step k of every chain (f, g, b) for one edge feature
-template <typename T>
+// small fixed-size vector of VB batch elements (VB = 4: one 16-byte access when B % 4 == 0 and T = float; else VB = 1)
+template <typename T, int VB>
+struct BVec {
+  T v[VB];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < VB; ++i) v[i] = T(0);
+  }
+};
+template <typename T, int VB>
+__device__ __forceinline__ BVec<T, VB> bload(const T* p) {
+  BVec<T, VB> r;
+  if constexpr (VB == 4 && sizeof(T) == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < VB; ++i) r.v[i] = p[i];
+  }
+  return r;
+}
+template <typename T, int VB>
+__device__ __forceinline__ void bstore(T* p, const BVec<T, VB>& a) {
+  if constexpr (VB == 4 && sizeof(T) == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < VB; ++i) p[i] = a.v[i];
+  }
+}
+
+// step k of every chain (f, g, b) for one edge feature; one thread owns (f, i, VB consecutive b) and loops over g
+template <typename T, int VB>
 __global__ void __launch_bounds__(256)
 step_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ diag,
             const T* __restrict__ w, const T* __restrict__ uprev, const T* __restrict__ xT, T* __restrict__ ucur,
-            T* __restrict__ Y, int64_t NA, int B, int G, int K, int k, int64_t nnz, int64_t total /* F*NA*B */) {
+            T* __restrict__ Y, int NA, int B, int G, int K, int k, int nnz, int64_t total /* F*NA*(B/VB) */) {
+  const int BV = B / VB;
+  const size_t plane = (size_t)NA * B;                       // one (f, g) state
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int b = (int)(t % B);
-    const int64_t fi = t / B;
-    const int64_t i = fi % NA;
-    const int64_t f = fi / NA;
-    const int64_t beg = rowptr[i], end = rowptr[i + 1];
-    T ysum = T(0);
-    for (int g = 0; g < G; ++g) {
-      const T* __restrict__ wk = w + ((f * K + k) * G + g) * nnz;
-      const T* __restrict__ up = (k == 0 ? xT + (int64_t)g * NA * B : uprev + (f * G + g) * NA * B) + b;
-      T acc = T(0);
-      if (k == 0 && diag) {
-        const int32_t d = diag[i];
-        if (d >= 0) acc = wk[d] * up[i * B];
+    const int b = (int)(t % BV) * VB;
+    const int64_t fi = t / BV;
+    const int i = (int)(fi % NA);
+    const int f = (int)(fi / NA);
+    const int beg = (int)rowptr[i], end = (int)rowptr[i + 1];
+    const int32_t d = (k == 0 && diag) ? diag[i] : -2;        // -2: ordinary sparse step
+    BVec<T, VB> ysum;
+    ysum.zero();
+    const T* __restrict__ wk = w + ((size_t)(f * K + k) * G) * nnz;                    // + g * nnz
+    const T* __restrict__ up = (k == 0 ? xT : uprev + (size_t)f * G * plane) + b;      // + g * plane
+    T* __restrict__ uc = ucur ? ucur + (size_t)f * G * plane + (size_t)i * B + b : nullptr;
+    for (int g = 0; g < G; ++g, wk += nnz, up += plane) {
+      BVec<T, VB> acc;
+      acc.zero();
+      if (d != -2) {
+        if (d >= 0) {
+          const T wv = wk[d];
+          const BVec<T, VB> u = bload<T, VB>(up + (size_t)i * B);
+#pragma unroll
+          for (int q = 0; q < VB; ++q) acc.v[q] = wv * u.v[q];
+        }
       } else {
-        for (int64_t idx = beg; idx < end; ++idx) acc = fma(wk[idx], up[(int64_t)col[idx] * B], acc);
+        for (int idx = beg; idx < end; ++idx) {
+          const T wv = wk[idx];
+          const BVec<T, VB> u = bload<T, VB>(up + (size_t)col[idx] * B);
+#pragma unroll
+          for (int q = 0; q < VB; ++q) acc.v[q] = fma(wv, u.v[q], acc.v[q]);
+        }
       }
-      if (ucur) ucur[((f * G + g) * NA + i) * B + b] = acc;
-      ysum += acc;
+      if (uc) { bstore<T, VB>(uc, acc); uc += plane; }
+#pragma unroll
+      for (int q = 0; q < VB; ++q) ysum.v[q] += acc.v[q];
     }
-    Y[t] = k == 0 ? ysum : Y[t] + ysum;
+    T* __restrict__ y = Y + ((size_t)f * NA + i) * B + b;
+    if (k != 0) {
+      const BVec<T, VB> old = bload<T, VB>(y);
+#pragma unroll
+      for (int q = 0; q < VB; ++q) ysum.v[q] += old.v[q];
+    }
+    bstore<T, VB>(y, ysum);
   }
 }
 
@@ -67,23 +120,30 @@ __global__ void adjoint_init_kernel(const T* __restrict__ dY, T* __restrict__ la
 }
 
 // lam_{k-1}[(f,g), j, b] = dY[f, j, b] + sum_{it in rowT(j)} w_k[perm[it]] * lam_k[(f,g), colT[it], b]        (k >= 1)
-template <typename T>
+template <typename T, int VB>
 __global__ void __launch_bounds__(256)
 adjoint_step_kernel(const int64_t* __restrict__ rowptrT, const int32_t* __restrict__ colT, const int64_t* __restrict__ perm,
                     const T* __restrict__ w, const T* __restrict__ dY, const T* __restrict__ lam_k, T* __restrict__ lam_km1,
-                    int64_t NA, int B, int G, int K, int k, int64_t nnz, int64_t total /* F*G*NA*B */) {
+                    int NA, int B, int G, int K, int k, int nnz, int64_t total /* F*G*NA*(B/VB) */) {
+  const int BV = B / VB;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int b = (int)(t % B);
-    const int64_t cj = t / B;
-    const int64_t j = cj % NA;
-    const int64_t fg = cj / NA;
-    const int64_t f = fg / G;
-    const int g = (int)(fg - f * G);
-    const T* __restrict__ wk = w + ((f * K + k) * G + g) * nnz;
-    const T* __restrict__ lk = lam_k + fg * NA * B + b;
-    T acc = dY[(f * NA + j) * B + b];
-    for (int64_t it = rowptrT[j]; it < rowptrT[j + 1]; ++it) acc = fma(wk[perm[it]], lk[(int64_t)colT[it] * B], acc);
-    lam_km1[t] = acc;
+    const int b = (int)(t % BV) * VB;
+    const int64_t cj = t / BV;
+    const int j = (int)(cj % NA);
+    const int fg = (int)(cj / NA);
+    const int f = fg / G;
+    const int g = fg - f * G;
+    const T* __restrict__ wk = w + ((size_t)(f * K + k) * G + g) * nnz;
+    const T* __restrict__ lk = lam_k + (size_t)fg * NA * B + b;
+    BVec<T, VB> acc = bload<T, VB>(dY + ((size_t)f * NA + j) * B + b);
+    const int beg = (int)rowptrT[j], end = (int)rowptrT[j + 1];
+    for (int it = beg; it < end; ++it) {
+      const T wv = wk[perm[it]];
+      const BVec<T, VB> l = bload<T, VB>(lk + (size_t)colT[it] * B);
+#pragma unroll
+      for (int q = 0; q < VB; ++q) acc.v[q] = fma(wv, l.v[q], acc.v[q]);
+    }
+    bstore<T, VB>(lam_km1 + ((size_t)fg * NA + j) * B + b, acc);
   }
 }
 
@@ -154,6 +214,15 @@ xgrad_kernel(const int64_t* __restrict__ rowptrT, const int32_t* __restrict__ co
 
 inline int grid_for(int64_t total) { return (int)imin64((total + 255) / 256, 148 * 16); }
 
+// 16-byte batch vectors: float data, B a multiple of 4, every operand 16-byte aligned (all row strides are multiples of B)
+template <typename T>
+inline bool vec4_ok(int B, const void* a, const void* b, const void* c, const void* d) {
+  if (sizeof(T) != 4 || B % 4 != 0) return false;
+  for (const void* p : {a, b, c, d})
+    if (p && (reinterpret_cast<uintptr_t>(p) & 15)) return false;
+  return true;
+}
+
 template <typename T>
 int forward_t(int64_t NA, int B, int G, int F, int K, const int64_t* rowptr, const int32_t* col, const int32_t* diag,
               int64_t nnz, const T* w, const T* xT, T* states, int n_states, T* Y, cudaStream_t st) {
@@ -165,7 +234,10 @@ int forward_t(int64_t NA, int B, int G, int F, int K, const int64_t* rowptr, con
     // (inference); the last step's state is never needed and is not written.
     const T* prev = k > 0 ? states + (int64_t)((k - 1) % n_states) * chain : nullptr;
     T* cur = k < K - 1 ? states + (int64_t)(k % n_states) * chain : nullptr;
-    step_kernel<T><<<grid_for(total), 256, 0, st>>>(rowptr, col, diag, w, prev, xT, cur, Y, NA, B, G, K, k, nnz, total);
+    if (vec4_ok<T>(B, w, xT, states, Y))
+      step_kernel<T, 4><<<grid_for(total / 4), 256, 0, st>>>(rowptr, col, diag, w, prev, xT, cur, Y, (int)NA, B, G, K, k, (int)nnz, total / 4);
+    else
+      step_kernel<T, 1><<<grid_for(total), 256, 0, st>>>(rowptr, col, diag, w, prev, xT, cur, Y, (int)NA, B, G, K, k, (int)nnz, total);
     LAUNCH_CHECK();
   }
   return B200GF_OK;
@@ -190,7 +262,10 @@ int backward_t(int64_t NA, int B, int G, int F, int K, const int64_t* rowptr, co
       LAUNCH_CHECK();
     }
     if (k == 0) break;
-    adjoint_step_kernel<T><<<grid_for(chain), 256, 0, st>>>(rowptrT, colT, perm, w, dY, cur, nxt, NA, B, G, K, k, nnz, chain);
+    if (vec4_ok<T>(B, dY, lam, lam, dY))
+      adjoint_step_kernel<T, 4><<<grid_for(chain / 4), 256, 0, st>>>(rowptrT, colT, perm, w, dY, cur, nxt, (int)NA, B, G, K, k, (int)nnz, chain / 4);
+    else
+      adjoint_step_kernel<T, 1><<<grid_for(chain), 256, 0, st>>>(rowptrT, colT, perm, w, dY, cur, nxt, (int)NA, B, G, K, k, (int)nnz, chain);
     LAUNCH_CHECK();
     T* tmp = cur; cur = nxt; nxt = tmp;
   }
@@ -211,6 +286,7 @@ int b200gf_ev_forward(int dtype, int64_t NA, int B, int G, int F, int K, const i
   using namespace b200gf;
   if (NA < 0 || B <= 0 || G <= 0 || F <= 0 || K <= 0 || nnz < 0) return B200GF_EINVAL;
   if (!rowptr || !col || !xT || !Y || (nnz > 0 && !w)) return B200GF_EINVAL;
+  if (NA > INT32_MAX || nnz > INT32_MAX) return B200GF_EUNSUPPORTED;
   if (K > 1 && (!states || n_states < 1 || (n_states < K - 1 && n_states != 2))) return B200GF_EINVAL;
   if (K > 2 && n_states == 1) return B200GF_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
@@ -231,6 +307,7 @@ int b200gf_ev_backward(int dtype, int64_t NA, int B, int G, int F, int K, const 
   if (NA < 0 || B <= 0 || G <= 0 || F <= 0 || K <= 0 || nnz < 0) return B200GF_EINVAL;
   if (!rowptr || !col || !rowptrT || !colT || !perm || !xT || !dY || !lam || !dxT || (K > 1 && !states)) return B200GF_EINVAL;
   if (nnz > 0 && (!w || !dw)) return B200GF_EINVAL;
+  if (NA > INT32_MAX || nnz > INT32_MAX) return B200GF_EUNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B200GF_F32)
     return ev::backward_t<float>(NA, B, G, F, K, rowptr, col, rowptrT, colT, perm, diag, nnz, (const float*)w, (const float*)xT,

@@ -18,6 +18,8 @@
 //   warps 6-9     epilogue: tcgen05.ld (32x32b), + bias, 16-byte stores of whole output rows.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200gf {
@@ -43,6 +45,7 @@ struct Params {
   int num_tiles;
   int stages;
   int bias_per_node;
+  int raw_hi;        // experiment (B200GF_TC_RAWHI=1): leave the TMA tile as the hi operand (valid iff the tensor core truncates FP32 -> TF32)
   int relu;          // epilogue activation: out = max(out, 0)  (fused GraphFilter -> ReLU layer, architectures.py:287)
 };
 
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_contract_kernel(const __grid_co
           float4 hi, lo;
           hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
           lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
-          A[idx] = hi;
+          if (!prm.raw_hi) A[idx] = hi;
           Alo[idx] = lo;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> visible to the tensor core
@@ -425,6 +428,10 @@ int launch_tc_contract(int sm_count, int64_t n_rows, int B, int P, int Q, int T,
   prm.stages = stages_for(Q);
   prm.bias_per_node = bias_per_node;
   prm.relu = act;
+  {
+    static const int raw = [] { const char* e = getenv("B200GF_TC_RAWHI"); return (e && e[0] == '1') ? 1 : 0; }();
+    prm.raw_hi = raw;
+  }
   const int stage_bytes = 2 * A_BYTES + 2 * Q * BK * 4;
   const size_t smem = (size_t)prm.stages * stage_bytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
   CUDA_TRY(cudaFuncSetAttribute(tc_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
