@@ -104,21 +104,19 @@ __device__ __forceinline__ Acc<T, VEC> load_vec(const T* p, uint64_t pol) {
 template <typename T, int VEC, int SH>
 __device__ __forceinline__ void store_vec(T* p, const Acc<T, VEC>& a) {
   if constexpr (VEC * sizeof(T) == 32 && sizeof(T) == 4) {
-    if constexpr (SH == 1) {
-      __stcs(reinterpret_cast<float4*>(p), make_float4(a.v[0], a.v[1], a.v[2], a.v[3]));
-      __stcs(reinterpret_cast<float4*>(p) + 1, make_float4(a.v[4], a.v[5], a.v[6], a.v[7]));
-    } else {
-      reinterpret_cast<float4*>(p)[0] = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
-      reinterpret_cast<float4*>(p)[1] = make_float4(a.v[4], a.v[5], a.v[6], a.v[7]);
-    }
+    // one 256-bit store per lane (STG.E.256): a row leaves as whole contiguous sectors — two 16-byte stores per lane
+    // would interleave half-sector writes across the warp, which costs on NVLink peer stores (fused all-gather epilogue)
+    if constexpr (SH == 1)
+      asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.v[0]), "f"(a.v[1]), "f"(a.v[2]),
+                   "f"(a.v[3]), "f"(a.v[4]), "f"(a.v[5]), "f"(a.v[6]), "f"(a.v[7]) : "memory");
+    else
+      asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.v[0]), "f"(a.v[1]), "f"(a.v[2]),
+                   "f"(a.v[3]), "f"(a.v[4]), "f"(a.v[5]), "f"(a.v[6]), "f"(a.v[7]) : "memory");
   } else if constexpr (VEC * sizeof(T) == 32) {
-    if constexpr (SH == 1) {
-      __stcs(reinterpret_cast<double2*>(p), make_double2(a.v[0], a.v[1]));
-      __stcs(reinterpret_cast<double2*>(p) + 1, make_double2(a.v[2], a.v[3]));
-    } else {
-      reinterpret_cast<double2*>(p)[0] = make_double2(a.v[0], a.v[1]);
-      reinterpret_cast<double2*>(p)[1] = make_double2(a.v[2], a.v[3]);
-    }
+    if constexpr (SH == 1)
+      asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a.v[0]), "d"(a.v[1]), "d"(a.v[2]), "d"(a.v[3]) : "memory");
+    else
+      asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a.v[0]), "d"(a.v[1]), "d"(a.v[2]), "d"(a.v[3]) : "memory");
   } else if constexpr (VEC == 4) {
     if constexpr (SH == 1) __stcs(reinterpret_cast<float4*>(p), make_float4(a.v[0], a.v[1], a.v[2], a.v[3]));
     else *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);

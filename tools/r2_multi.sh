@@ -31,10 +31,13 @@ except Exception as e:
   tail -3 $OUT/bench_$name.err | cut -c1-300
 }
 run auto
-run nodes_ipc --mode nodes --symm ipc --no-selftest
-run features --mode features --no-selftest
 if [ -z "$QUICK" ]; then
+  run nodes_ipc --mode nodes --symm ipc --no-selftest
+  run features --mode features --no-selftest
   run nodes_nograph --mode nodes --no-graph --no-selftest --no-bwd
   run er2m --workload er2m --mode nodes --no-selftest
+else
+  run nodes --mode nodes --no-selftest
+  run er2m --workload er2m --mode auto --no-selftest
 fi
 ls $OUT
