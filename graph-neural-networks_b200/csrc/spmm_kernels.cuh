@@ -413,6 +413,81 @@ spmm_hop_v2_kernel(const IDX* __restrict__ rowptr, const int32_t* __restrict__ c
   }
 }
 
+// Narrow rows with the v2 treatment (32-bit index math, 32-byte lanes, epilogue selected at compile time): a warp works on
+// RPW = 32/GS consecutive rows at once, each group of GS lanes owns one row and its S = GS/L sub-groups of L lanes gather S
+// neighbours per load.  C = 8 floats: L = 1 — one lane fetches a whole 32-byte neighbour row.
+template <typename T, typename IDX, int VEC, int L, int GS, int U, int THREADS, int MINB, int HINT, int SCATTER>
+__global__ void __launch_bounds__(THREADS, MINB)
+spmm_hop_multirow_v2_kernel(const IDX* __restrict__ rowptr, const int32_t* __restrict__ col, const T* __restrict__ val,
+                            const T* __restrict__ src, int src_ld, T* __restrict__ dst, int dst_ld, int n_rows, int C,
+                            const ScatterParam<T, SCATTER> sp) {
+  static_assert(GS % L == 0 && GS <= 32 && (GS / L) * U <= GS, "bad multirow geometry");
+  constexpr int RPW = 32 / GS;
+  constexpr int S = GS / L;
+  uint64_t pol = 0;
+  if constexpr (HINT >= 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  const int lane = threadIdx.x & 31;
+  const int grp = lane / GS, gl = lane % GS;
+  const int sub = gl / L, cl = gl % L;
+  const int cbase = cl * VEC;
+  const bool col_ok = cbase < C;
+  const T* __restrict__ srcc = src + cbase;
+  const int n_warps = gridDim.x * (THREADS >> 5);
+  for (int row0 = (blockIdx.x * (THREADS >> 5) + (threadIdx.x >> 5)) * RPW; row0 < n_rows; row0 += n_warps * RPW) {
+    const int row = row0 + grp;
+    const bool row_ok = row < n_rows;
+    const IDX beg = row_ok ? __ldg(rowptr + row) : 0;
+    const int len = row_ok ? (int)(__ldg(rowptr + row + 1) - beg) : 0;
+    int maxlen = len;  // warp-uniform trip count: the longest of the RPW rows
+#pragma unroll
+    for (int off = GS; off < 32; off <<= 1) maxlen = max(maxlen, __shfl_xor_sync(FULL, maxlen, off));
+    Acc<T, VEC> acc;
+    acc.zero();
+    for (int b0 = 0; b0 < maxlen; b0 += GS) {
+      int32_t c = 0;
+      T v = T(0);
+      if (b0 + gl < len) { c = ld_stream(col + beg + b0 + gl); v = ld_stream(val + beg + b0 + gl); }
+      const int cnt = len - b0;           // entries of my row left in this chunk (may be <= 0)
+      const int maxcnt = maxlen - b0;
+#pragma unroll
+      for (int j = 0; j < GS; j += S * U) {
+        if (j >= maxcnt) break;           // warp-uniform
+        Acc<T, VEC> buf[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int jj = j + u * S + sub;
+          const int32_t cc = __shfl_sync(FULL, c, jj, GS);
+          if ((jj < cnt) && col_ok) buf[u] = load_vec<T, VEC, HINT>(srcc + (int64_t)cc * src_ld, pol);
+          else buf[u].zero();
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int jj = j + u * S + sub;
+          const T ww = __shfl_sync(FULL, v, jj, GS);
+          const T w = jj < cnt ? ww : T(0);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc.v[i] = fma(w, buf[u].v[i], acc.v[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int off = L; off < GS; off <<= 1) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc.v[i] += __shfl_xor_sync(FULL, acc.v[i], off);
+    }
+    if (sub == 0 && col_ok && row_ok) {
+      if constexpr (SCATTER == EPI_BCAST) {
+        bcast_store<T, VEC>(sp.a, row, cbase, acc);
+      } else {
+        store_vec<T, VEC, 0>(dst + (int64_t)row * dst_ld + cbase, acc);
+        if constexpr (SCATTER == EPI_SCATTER) {
+          if (sp.a.n_peers > 0) scatter_store<T, VEC>(sp.a, row, cbase, acc);
+        }
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g, uint64_t pol, bool hint) {
   if (hint)
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(saddr), "l"(g), "l"(pol) : "memory");

@@ -190,6 +190,18 @@ double run_mr(const Problem& P, const char* name, int reps, double peak) {
   return avg;
 }
 
+// multi-row kernel with 32-byte lanes (VEC = 8)
+template <int L, int GS, int U, int MINB, int HINT, int VEC = 8>
+double run_mr_w(const Problem& P, const char* name, int reps, double peak) {
+  constexpr int THREADS = 256;
+  auto kern = spmm_hop_multirow_v2_kernel<float, int32_t, VEC, L, GS, U, THREADS, MINB, HINT, 0>;
+  const int rpw = 32 / GS;
+  const int64_t warps_needed = (P.N + rpw - 1) / rpw;
+  return time_variant(P, name, reps, peak, kern, THREADS, 0, 0, (warps_needed + 7) / 8, [&](unsigned blocks) {
+    kern<<<blocks, THREADS>>>(P.rowptr32, P.col, P.val, P.src, P.C, P.dst, P.C, (int)P.N, P.C, ScatterParam<float, 0>{});
+  });
+}
+
 int main(int argc, char** argv) {
   const int64_t N = argc > 1 ? atoll(argv[1]) : 1000000;
   const int deg = argc > 2 ? atoi(argv[2]) : 32;
@@ -256,7 +268,33 @@ int main(int argc, char** argv) {
 #define ADDW(NAME, FRAC, ...) vs.push_back(V{NAME, [&](bool) { return run_v2w<__VA_ARGS__>(P, NAME, reps, peak, FRAC); }, {0, 0, 0}})
 #define ADDMR(NAME, ...) vs.push_back(V{NAME, [&](bool) { return run_mr<__VA_ARGS__>(P, NAME, reps, peak); }, {0, 0, 0}})
   //                                  L  GS  U MINB HINT
-  if (C <= 8) {           // feature-sharded multi-GPU slices: 32-byte rows
+#define ADDMRW(NAME, ...) vs.push_back(V{NAME, [&](bool) { return run_mr_w<__VA_ARGS__>(P, NAME, reps, peak); }, {0, 0, 0}})
+  if (C <= 16 && getenv("SWEEP_R2")) {   // narrow rows with 32-byte lanes (feature-sharded slices at 4 / 8 GPUs)
+    if (C <= 8) {
+      ADDMR("r1 mrow L2 GS8  U2 EL mb6",  2, 8, 2, 6, 3);
+      ADDMRW("w mrow L1 GS8  U1 mb6",     1, 8, 1, 6, 3);
+      ADDMRW("w mrow L1 GS8  U1 mb8",     1, 8, 1, 8, 3);
+      ADDMRW("w mrow L1 GS4  U1 mb8",     1, 4, 1, 8, 3);
+      ADDMRW("w mrow L1 GS16 U1 mb6",     1, 16, 1, 6, 3);
+      ADDMRW("w mrow L1 GS32 U1 mb8",     1, 32, 1, 8, 3);
+      ADDMRW("w mrow L1 GS8  U1 mb8 noEL", 1, 8, 1, 8, 1);
+      ADDMRW("v2-16B mrow L2 GS8 U2 mb6",  2, 8, 2, 6, 3, 4);
+      ADDMRW("w mrow L1 GS8  U1 mb5",     1, 8, 1, 5, 3);
+      ADDMRW("w mrow L1 GS8  U1 mb4",     1, 8, 1, 4, 3);
+      ADDMRW("w mrow L1 GS16 U1 mb4",     1, 16, 1, 4, 3);
+    } else {
+      ADDMR("r1 mrow L4 GS16 U2 EL mb8",  4, 16, 2, 8, 3);
+      ADDMRW("w mrow L2 GS16 U2 mb6",     2, 16, 2, 6, 3);
+      ADDMRW("w mrow L2 GS16 U1 mb8",     2, 16, 1, 8, 3);
+      ADDMRW("w mrow L2 GS8  U1 mb8",     2, 8, 1, 8, 3);
+      ADDMRW("w mrow L2 GS32 U2 mb6",     2, 32, 2, 6, 3);
+      ADDMRW("w mrow L2 GS16 U2 mb6 noEL", 2, 16, 2, 6, 1);
+      ADDMRW("v2-16B mrow L4 GS16 U2 mb8", 4, 16, 2, 8, 3, 4);
+      ADDMRW("w mrow L2 GS16 U2 mb4",     2, 16, 2, 4, 3);
+      ADDMRW("w mrow L2 GS16 U1 mb5",     2, 16, 1, 5, 3);
+      ADDMRW("w mrow L2 GS8  U2 mb4",     2, 8, 2, 4, 3);
+    }
+  } else if (C <= 8) {           // feature-sharded multi-GPU slices: 32-byte rows
     ADD("1row  L2 U2 EL mb6",          2, 2, 256, 6, 3, false);
     ADDMR("mrow L2 GS4  U2 EL mb6",    2, 4, 2, 6, 3);
     ADDMR("mrow L2 GS8  U2 EL mb6",    2, 8, 2, 6, 3);
