@@ -252,6 +252,7 @@ def oracle_forward_nm(gso, h, b, x_nm, B, G):
     node-major x [N, B*G]; returns y node-major [N, B*F] float64."""
     import scipy.sparse as sp
     import lsigf_oracle as orc
+    torch.set_num_threads(usable_cores())       # torchrun exports OMP_NUM_THREADS=1; the check runs on rank 0 only
     N = gso.N
     S = [sp.csr_matrix((v.astype(np.float64), c, r), shape=(N, N)) for (r, c, v) in gso.csr]
     x = x_nm.double().numpy().reshape(N, B, G).transpose(1, 2, 0)                         # [B, G, N]
@@ -462,17 +463,10 @@ def single_gpu_workload(ctx, name, w, steps, warmup, full):
     lib.b200gf_profile_hops(plan.handle, cap)
     with torch.no_grad(), ClockSampler(ctx.local) as clk:
         ms, launches = ctx.timed(fwd, steps, warmup)
-    all_ms = ctypes_floats(lib, plan, cap)
+    hop_ms = ctypes_floats(lib, plan, cap)[hops * warmup:]   # launches inside the timed region only
     lib.b200gf_profile_hops(plan.handle, 0)
-    chained = hops > E and len(all_ms) == E * (steps + warmup)   # small graphs: the K-1 hops of a chain are ONE launch
-    per_step = E if chained else hops
-    hop_ms = all_ms[per_step * warmup:]                      # launches inside the timed region only
-    kname = "hop_chain_kernel (%d hops per launch, sources in shared memory)" % (K - 1) if chained else \
-        ("spmm_hop_v2_kernel" if B * G * es > 128 else "spmm_hop_multirow_kernel")
-    rf = hop_roofline(ctx, hop_ms, ms * steps, nnz_e, N, B * G, kname, workload=name)
-    if rf and chained:                                       # one launch moves K-1 hops' worth of algorithmic bytes
-        for k in ("achieved", "frac", "bytes_per_launch"):
-            rf[k] *= (K - 1)
+    rf = hop_roofline(ctx, hop_ms, ms * steps, nnz_e, N, B * G, "spmm_hop_v2_kernel" if B * G * es > 128
+                      else "spmm_hop_multirow_kernel", workload=name)
     out = {"ms_per_step": ms, "value": ops_per_step / (ms * 1e-3), "unit": "edge-feature-op/s", "nnz": gso.nnz(),
            "ops_per_step": ops_per_step, "gpu_launches": launches, "clocks": clk.summary(), "roofline": rf}
     if not args.no_check:

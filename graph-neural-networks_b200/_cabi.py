@@ -42,7 +42,6 @@ _SIGNATURES = {
     "b200gf_profile_hops": (c_int, [c_vp, c_int]),
     "b200gf_profile_read": (c_int, [c_vp, ctypes.POINTER(ctypes.c_float), c_int]),
     "b200gf_hop": (c_int, [c_vp, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_int, c_vp]),
-    "b200gf_hop_chain": (c_int, [c_vp, c_int, c_int, c_vp, c_i64, PP, c_i64, c_int, c_int, c_vp]),
     "b200gf_hop_scatter": (c_int, [c_vp, c_int, c_int, c_vp, c_i64, c_vp, c_i64, c_int, PP, c_int, c_i64, c_i64, c_i64,
                                    c_int, c_i64, c_vp]),
     "b200gf_scatter_rows": (c_int, [c_int, c_vp, c_i64, c_i64, c_int, PP, c_int, c_i64, c_i64, c_i64, c_int, c_i64, c_vp]),

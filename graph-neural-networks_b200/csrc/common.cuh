@@ -73,12 +73,6 @@ int launch_scatter_rows(int dtype, const void* src, int64_t src_ld, int64_t n_ro
 int launch_bcast_rows(int dtype, const void* src, int64_t src_ld, int64_t n_rows, int C, cudaStream_t st,
                       const BcastHost* bh);
 
-// all hops of one chain in one launch for small graphs (chain.cu)
-bool hop_chain_eligible(int dtype, const CsrDev& A, int64_t n_rows, int64_t n_cols, const void* src, int64_t src_ld,
-                        void* const* dst, int64_t dst_ld, int C, int n_hops);
-int launch_hop_chain(int dtype, const CsrDev& A, int64_t n_rows, const void* src, int64_t src_ld, void* const* dst,
-                     int64_t dst_ld, int C, int n_hops, cudaStream_t st);
-
 struct TermList {            // passed by value to kernels: up to MAX_TERMS (pointer, ld) pairs
   static constexpr int MAX_TERMS = 48;
   const void* ptr[MAX_TERMS];
@@ -144,6 +138,4 @@ namespace b200gf {
 // hop launch of forward/backward, bracketed with events when profiling is on
 int plan_hop(const b200gf_plan* p, const CsrDev& A, const void* src, int64_t src_ld, void* dst, int64_t dst_ld, int C,
              cudaStream_t st, const ScatterHost* sh = nullptr, const BcastHost* bh = nullptr);
-int plan_chain(const b200gf_plan* p, const CsrDev& A, const void* src, int64_t src_ld, void* const* dst, int64_t dst_ld, int C,
-               int n_hops, cudaStream_t st);
 }

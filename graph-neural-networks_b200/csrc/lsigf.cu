@@ -96,18 +96,6 @@ int plan_hop(const b200gf_plan* p, const CsrDev& A, const void* src, int64_t src
   }
   return rc;
 }
-// the whole chain of one edge feature in one launch (chain.cu); one event pair for the launch when profiling is on
-int plan_chain(const b200gf_plan* p, const CsrDev& A, const void* src, int64_t src_ld, void* const* dst, int64_t dst_ld, int C,
-               int n_hops, cudaStream_t st) {
-  const bool prof = p->prof_used < (int)p->prof_start.size();
-  if (prof) CUDA_TRY(cudaEventRecord(p->prof_start[p->prof_used], st));
-  const int rc = launch_hop_chain(p->dtype, A, p->n_rows, src, src_ld, dst, dst_ld, C, n_hops, st);
-  if (prof) {
-    CUDA_TRY(cudaEventRecord(p->prof_stop[p->prof_used], st));
-    p->prof_used++;
-  }
-  return rc;
-}
 }  // namespace b200gf
 
 extern "C" {
@@ -190,11 +178,6 @@ static int forward_impl(const b200gf_plan* plan, const void* x, int x_layout, in
       chain[k - 1] = (char*)w.z + (size_t)(t - 1) * N * ldc * es;
       zs[t] = chain[k - 1];
       zld[t] = ldc;
-    }
-    // small graphs: the whole chain in one launch, hops reading their source from shared memory (chain.cu)
-    if (hop_chain_eligible(dt, plan->fwd[e], N, plan->n_cols, x0, x0_ld, chain.data(), ldc, (int)C, K - 1)) {
-      if ((rc = plan_chain(plan, plan->fwd[e], x0, x0_ld, chain.data(), ldc, (int)C, K - 1, st))) return rc;
-      continue;
     }
     const void* prev = x0;
     int64_t prev_ld = x0_ld;
@@ -292,10 +275,6 @@ int b200gf_backward(const b200gf_plan* plan, const void* dy, int dy_layout, int6
       chain[k - 1] = (char*)w.v + (size_t)(t - 1) * N * ldf * es;
       vs[t] = chain[k - 1];
       vld[t] = ldf;
-    }
-    if (hop_chain_eligible(dt, plan->bwd[e], N, plan->n_cols, dy0, dy0_ld, chain.data(), ldf, (int)CF, K - 1)) {
-      if ((rc = plan_chain(plan, plan->bwd[e], dy0, dy0_ld, chain.data(), ldf, (int)CF, K - 1, st))) return rc;
-      continue;
     }
     const void* prev = dy0;
     int64_t prev_ld = dy0_ld;

@@ -130,6 +130,30 @@ static int launch_v2_sc(int sm_count, const CsrDev& A, int64_t n_rows, const T* 
   return launch_v2<T, L, EPI_NONE>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, nullptr, nullptr);
 }
 
+// 64-byte rows (C = 16 floats / 8 doubles) with 32-byte lanes: two lanes per neighbour row, 8-lane row groups, two loads in
+// flight per lane — 0.267 ms against 0.337 ms for the 16-byte-lane kernel at N = 1M (profiles/r2_spmm_sweep_narrow_c16.log);
+// at C = 8 the 32-byte lanes bring nothing (0.20 vs 0.19 ms), those rows stay on spmm_hop_multirow_kernel.
+template <typename T, int SCATTER>
+static int launch_multirow_v2(int sm_count, const CsrDev& A, int64_t n_rows, const T* src, int64_t src_ld, T* dst,
+                              int64_t dst_ld, int C, cudaStream_t st, const ScatterHost* sh) {
+  constexpr int VEC = 32 / sizeof(T), L = 2, GS = 8, U = 2, THREADS = 256, MINB = 3, HINT = 3;
+  auto kern = spmm_hop_multirow_v2_kernel<T, int32_t, VEC, L, GS, U, THREADS, MINB, HINT, SCATTER>;
+  if (n_rows == 0) return B200GF_OK;
+  constexpr int rows_per_block = (THREADS / 32) * (32 / GS);
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, 0));
+  if (occ < 1) occ = 1;
+  int64_t blocks = (n_rows + rows_per_block - 1) / rows_per_block;
+  const int64_t cap = (int64_t)sm_count * occ;
+  if (blocks > cap) blocks = cap;
+  ScatterParam<T, SCATTER> sp{};
+  if constexpr (SCATTER == EPI_SCATTER) sp.a = make_scatter<T>(sh);
+  kern<<<(unsigned)blocks, THREADS, 0, st>>>(A.rowptr32, A.col, reinterpret_cast<const T*>(A.val), src, (int)src_ld, dst,
+                                             (int)dst_ld, (int)n_rows, C, sp);
+  LAUNCH_CHECK();
+  return B200GF_OK;
+}
+
 template <typename T>
 static int launch_typed(int sm_count, const CsrDev& A, int64_t n_rows, const void* src_, int64_t src_ld,
                         void* dst_, int64_t dst_ld, int C, cudaStream_t st, const ScatterHost* sh, const BcastHost* bh) {
@@ -161,6 +185,19 @@ static int launch_typed(int sm_count, const CsrDev& A, int64_t n_rows, const voi
     return B200GF_EUNSUPPORTED;
   const int nv = Cv / VEC;  // 16-byte vectors per row
   constexpr int MB = sizeof(T) == 4 ? 6 : 4;
+  {
+    // exactly-64-byte rows: the 32-byte-lane multi-row kernel when its preconditions hold
+    constexpr int VW2 = 32 / sizeof(T);
+    bool w2 = nv > 2 && nv <= 4 && A.rowptr32 != nullptr && src_ld % VW2 == 0 && dst_ld % VW2 == 0 && 2 * VW2 <= src_ld &&
+              2 * VW2 <= dst_ld && (reinterpret_cast<uintptr_t>(src) & 31) == 0 && (reinterpret_cast<uintptr_t>(dst) & 31) == 0 &&
+              src_ld <= INT32_MAX && dst_ld <= INT32_MAX && n_rows <= INT32_MAX;
+    if (sh && sh->n_peers > 0)
+      w2 = w2 && sh->gl % VW2 == 0 && sh->out_ld % VW2 == 0 && sh->out_col % VW2 == 0 && sh->stride_b % VW2 == 0;
+    if (w2) {
+      if (sh && sh->n_peers > 0) return launch_multirow_v2<T, EPI_SCATTER>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);
+      return launch_multirow_v2<T, EPI_NONE>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, nullptr);
+    }
+  }
   if (nv <= 1) return launch_multirow<T, VEC, 1, 8, 1, MB>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);
   if (nv <= 2) return launch_multirow<T, VEC, 2, 8, 2, MB>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);
   if (nv <= 4) return launch_multirow<T, VEC, 4, 16, 2, sizeof(T) == 4 ? 8 : 4>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh);

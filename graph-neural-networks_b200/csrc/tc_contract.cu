@@ -10,8 +10,9 @@
 // One persistent CTA per SM, 320 threads, warp-specialised:
 //   warp 0        TMA producer: per 32-float k-chunk, one 128 x 32 tile of Z_t (128-byte swizzle) + the matching
 //                 Q x 32 tiles of W_hi and W_lo (pre-split, K-major) into a 4-stage shared-memory ring
-//   warps 2-5     splitter: rewrites the Z tile in place as hi and writes lo next to it (same swizzled layout:
-//                 the transform is element-wise), fence.proxy.async, then hands the stage to
+//   warps 2-5     splitter: writes lo = z - hi(z) next to the Z tile (same swizzled layout: the transform is
+//                 element-wise); the tile itself serves as the hi operand (the MMA truncates FP32 to TF32, which is
+//                 exactly hi), fence.proxy.async, then hands the stage to
 //   warp 1        MMA issuer: one elected lane issues 3 x 4 tcgen05.mma (M=128, N=Q, K=8) per stage into one of
 //                 two TMEM accumulators (so the epilogue of tile i overlaps the MMAs of tile i+1); tcgen05.commit
 //                 releases the stage to the producer and, after the last chunk, the accumulator to
@@ -45,7 +46,9 @@ struct Params {
   int num_tiles;
   int stages;
   int bias_per_node;
-  int raw_hi;        // experiment (B200GF_TC_RAWHI=1): leave the TMA tile as the hi operand (valid iff the tensor core truncates FP32 -> TF32)
+  int raw_hi;        // leave the TMA tile in place as the hi operand: the tensor core reads the top 19 bits of an FP32 value
+                     // (truncation), which IS hi — measured bit-identical to rewriting it (profiles/README.md), 16 KB less
+                     // shared-memory traffic per stage.  B200GF_TC_RAWHI=0 restores the rewrite.
   int relu;          // epilogue activation: out = max(out, 0)  (fused GraphFilter -> ReLU layer, architectures.py:287)
 };
 
@@ -429,7 +432,7 @@ int launch_tc_contract(int sm_count, int64_t n_rows, int B, int P, int Q, int T,
   prm.bias_per_node = bias_per_node;
   prm.relu = act;
   {
-    static const int raw = [] { const char* e = getenv("B200GF_TC_RAWHI"); return (e && e[0] == '1') ? 1 : 0; }();
+    static const int raw = [] { const char* e = getenv("B200GF_TC_RAWHI"); return (e && e[0] == '0') ? 0 : 1; }();
     prm.raw_hi = raw;
   }
   const int stage_bytes = 2 * A_BYTES + 2 * Q * BK * 4;

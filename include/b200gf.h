@@ -150,7 +150,7 @@ size_t b200gf_workspace_bytes(const b200gf_plan* plan, int B, int G, int F, int 
 
 /* Measurement hook (bench.py): b200gf_profile_hops(plan, capacity) makes b200gf_forward / b200gf_backward bracket
  * each of their next `capacity` hop launches with CUDA events on the launching stream (capacity 0 turns it off and
- * frees the events; a chain that runs as ONE launch — b200gf_hop_chain — counts as one).  b200gf_profile_read synchronises those events, writes up to n per-launch durations in ms
+ * frees the events).  b200gf_profile_read synchronises those events, writes up to n per-launch durations in ms
  * (launch order) and resets the counter; returns how many were written, or <0 on error. */
 int b200gf_profile_hops(b200gf_plan* plan, int capacity);
 int b200gf_profile_read(b200gf_plan* plan, float* ms, int n);
@@ -164,14 +164,6 @@ int b200gf_profile_read(b200gf_plan* plan, float* ms, int n);
  * src has n_cols rows of stride src_ld, dst has n_rows rows of stride dst_ld. */
 int b200gf_hop(const b200gf_plan* plan, int e, int direction,
                const void* src, int64_t src_ld, void* dst, int64_t dst_ld, int C, void* stream);
-
-/* n_hops consecutive shifts in ONE launch for small square operators (2 * N * 64 bytes of shared memory must fit 227 KB,
- * i.e. N <= ~1770): dst[0] = A src, dst[h] = A dst[h-1]; every hop reads its source from a shared-memory copy of its
- * 64-byte column slab, so the gathered rows never travel through L2 again.  b200gf_forward / _backward use it on their
- * own when it applies; returns B200GF_EUNSUPPORTED when it does not (use b200gf_hop then).  dst: HOST array of n_hops
- * device pointers, all [n_rows, dst_ld]; C, src_ld, dst_ld multiples of 4 floats / 2 doubles, 16-byte aligned. */
-int b200gf_hop_chain(const b200gf_plan* plan, int e, int direction, const void* src, int64_t src_ld,
-                     void* const* dst, int64_t dst_ld, int C, int n_hops, void* stream);
 
 /* Fused hop + collective for the feature-sharded multi-GPU path (one compute step followed by an exchange becomes
  * one kernel): as b200gf_hop, and additionally every computed row slice is stored over NVLink straight into the

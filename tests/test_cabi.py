@@ -136,52 +136,6 @@ def test_hop_building_block(C, dtype):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("C", [4, 16, 40, 64, 2048])
-@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
-def test_hop_chain_building_block(C, dtype):
-    """b200gf_hop_chain (all hops of a chain in one launch, sources in shared memory; csrc/chain.cu) against repeated
-    scipy products: slabs with a ragged tail (C = 40), a single narrow slab, many slabs (C = 2048), both directions,
-    empty rows, rows longer than one 32-entry window; and the size beyond which it must decline."""
-    import ctypes
-    import scipy.sparse as sp
-    import gnn_b200
-    cabi = gnn_b200._cabi
-    lib = cabi.load()
-    N, hops = 1500, 4
-    rs = np.random.RandomState(C + 1)
-    m = sp.random(N, N, density=0.012, format="lil", random_state=rs)
-    m[5, :] = 0
-    m[11, rs.choice(N, 90, replace=False)] = rs.randn(90)
-    m[rs.choice(N, 70, replace=False), 13] = rs.randn(70)[:, None]
-    m = sp.csr_matrix(m)
-    m = m / max(abs(m).sum(axis=1).max(), 1e-30)
-    m = sp.csr_matrix(m)
-    gso = gnn_b200.SparseGSO.from_scipy([m], dtype=dtype)
-    plan = gso.plan("cuda")
-    npd = np.float32 if dtype == torch.float32 else np.float64
-    mr = sp.csr_matrix((m.data.astype(npd).astype(np.float64), m.indices, m.indptr), shape=m.shape)
-    ld = gnn_b200.padded_ld(C, dtype)
-    X = torch.randn(N, C, dtype=dtype, device="cuda")
-    src = torch.zeros(N, ld, dtype=dtype, device="cuda"); src[:, :C] = X
-    st = torch.cuda.current_stream().cuda_stream
-    tol = 1e-5 if dtype == torch.float32 else 1e-13
-    for direction, op in ((cabi.HOP_FWD, mr.T.tocsr()), (cabi.HOP_BWD, mr)):
-        dst = [torch.full((N, ld), float("nan"), dtype=dtype, device="cuda") for _ in range(hops)]
-        rc = lib.b200gf_hop_chain(plan.handle, 0, direction, src.data_ptr(), ld, cabi.ptr_array([d.data_ptr() for d in dst]),
-                                  ld, C, hops, st)
-        assert rc == 0, lib.b200gf_strerror(rc)
-        ref = X.double().cpu().numpy()
-        for h in range(hops):
-            ref = op @ ref
-            assert _rel(dst[h][:, :C].cpu().numpy(), ref) < tol * (h + 1), (C, direction, h)
-    # too many nodes for two 64-byte slab buffers in 227 KB: declines, the caller falls back to b200gf_hop
-    big = gnn_b200.SparseGSO.from_scipy([sp.identity(4000, format="csr")], dtype=dtype).plan("cuda")
-    buf = torch.zeros(4000, ld, dtype=dtype, device="cuda")
-    rc = lib.b200gf_hop_chain(big.handle, 0, cabi.HOP_FWD, buf.data_ptr(), ld, cabi.ptr_array([buf.data_ptr()] * 2), ld, C, 2, st)
-    assert rc == -2                                              # B200GF_EUNSUPPORTED
-
-
-@pytest.mark.gpu
 def test_layout_and_tap_blocks():
     import gnn_b200
     cabi = gnn_b200._cabi

@@ -271,6 +271,7 @@ int main(int argc, char** argv) {
 #define ADDMRW(NAME, ...) vs.push_back(V{NAME, [&](bool) { return run_mr_w<__VA_ARGS__>(P, NAME, reps, peak); }, {0, 0, 0}})
   if (C <= 16 && getenv("SWEEP_R2")) {   // narrow rows with 32-byte lanes (feature-sharded slices at 4 / 8 GPUs)
     if (C <= 8) {
+      ADD("1row  L2 U2 EL mb6 (ref)",     2, 2, 256, 6, 3, false);
       ADDMR("r1 mrow L2 GS8  U2 EL mb6",  2, 8, 2, 6, 3);
       ADDMRW("w mrow L1 GS8  U1 mb6",     1, 8, 1, 6, 3);
       ADDMRW("w mrow L1 GS8  U1 mb8",     1, 8, 1, 8, 3);
@@ -283,6 +284,7 @@ int main(int argc, char** argv) {
       ADDMRW("w mrow L1 GS8  U1 mb4",     1, 8, 1, 4, 3);
       ADDMRW("w mrow L1 GS16 U1 mb4",     1, 16, 1, 4, 3);
     } else {
+      ADD("1row  L4 U2 EL mb6 (ref)",     4, 2, 256, 6, 3, false);
       ADDMR("r1 mrow L4 GS16 U2 EL mb8",  4, 16, 2, 8, 3);
       ADDMRW("w mrow L2 GS16 U2 mb6",     2, 16, 2, 6, 3);
       ADDMRW("w mrow L2 GS16 U1 mb8",     2, 16, 1, 8, 3);
@@ -293,6 +295,8 @@ int main(int argc, char** argv) {
       ADDMRW("w mrow L2 GS16 U2 mb4",     2, 16, 2, 4, 3);
       ADDMRW("w mrow L2 GS16 U1 mb5",     2, 16, 1, 5, 3);
       ADDMRW("w mrow L2 GS8  U2 mb4",     2, 8, 2, 4, 3);
+      ADDMRW("w mrow L2 GS8  U2 mb3",     2, 8, 2, 3, 3);
+      ADDMRW("w mrow L2 GS8  U2 mb5",     2, 8, 2, 5, 3);
     }
   } else if (C <= 8) {           // feature-sharded multi-GPU slices: 32-byte rows
     ADD("1row  L2 U2 EL mb6",          2, 2, 256, 6, 3, false);
