@@ -27,6 +27,7 @@ _SIGNATURES = {
     "b200gf_launch_count": (c_i64, [c_int]),
     "b200gf_plan_create": (c_int, [PP, c_int, c_i64, c_int, PP, PP, PP, c_int]),
     "b200gf_plan_create_ops": (c_int, [PP, c_int, c_i64, c_i64, c_int, PP, PP, PP, PP, PP, PP, c_int]),
+    "b200gf_plan_create_device": (c_int, [PP, c_int, c_i64, c_int, PP, PP, PP, PP, PP, PP, c_int]),
     "b200gf_plan_destroy": (None, [c_vp]),
     "b200gf_plan_info": (c_i64, [c_vp, c_int]),
     "b200gf_forward": (c_int, [c_vp, c_vp, c_int, c_i64, c_vp, c_vp, c_int, c_vp, c_int, c_i64, c_vp, c_sz,

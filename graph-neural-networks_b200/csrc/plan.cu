@@ -246,6 +246,67 @@ int b200gf_plan_create_ops(b200gf_plan** out, int device, int64_t n_rows, int64_
   return B200GF_OK;
 }
 
+// Device-side plan build: the caller already holds both gather operators as DEVICE CSR arrays (e.g. built with a few
+// sort / scan kernels for a GSO that changes every batch — LSIGF_DB's space-time operator); they are copied device to
+// device into plan-owned memory, nothing travels through the host except the two 8-byte nnz counts.
+namespace {
+__global__ void narrow_rowptr_kernel(const int64_t* __restrict__ in, int32_t* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (int32_t)in[i];
+}
+
+int adopt(const int64_t* rowptr, const int32_t* col, const void* val, int64_t n_rows, size_t es, CsrDev& D) {
+  if (!rowptr) return B200GF_EINVAL;
+  int64_t nnz = 0;
+  CUDA_TRY(cudaMemcpy(&nnz, rowptr + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  if (nnz < 0 || (nnz > 0 && (!col || !val))) return B200GF_EINVAL;
+  D.nnz = nnz;
+  D.owned = true;
+  if (cudaMalloc(&D.rowptr, (size_t)(n_rows + 1) * sizeof(int64_t)) != cudaSuccess) return B200GF_ENOMEM;
+  if (cudaMalloc(&D.col, (size_t)(nnz + 1) * sizeof(int32_t)) != cudaSuccess) return B200GF_ENOMEM;
+  if (cudaMalloc(&D.val, (size_t)(nnz + 1) * es) != cudaSuccess) return B200GF_ENOMEM;
+  CUDA_TRY(cudaMemcpy(D.rowptr, rowptr, (size_t)(n_rows + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice));
+  if (nnz > 0) {
+    CUDA_TRY(cudaMemcpy(D.col, col, (size_t)nnz * sizeof(int32_t), cudaMemcpyDeviceToDevice));
+    CUDA_TRY(cudaMemcpy(D.val, val, (size_t)nnz * es, cudaMemcpyDeviceToDevice));
+  }
+  if (nnz < (int64_t)INT32_MAX) {
+    if (cudaMalloc(&D.rowptr32, (size_t)(n_rows + 1) * sizeof(int32_t)) != cudaSuccess) return B200GF_ENOMEM;
+    narrow_rowptr_kernel<<<(int)imin64((n_rows + 256) / 256, 1184), 256>>>(D.rowptr, D.rowptr32, n_rows + 1);
+    LAUNCH_CHECK();
+  }
+  return B200GF_OK;
+}
+}  // namespace
+
+int b200gf_plan_create_device(b200gf_plan** out, int device, int64_t N, int E, const int64_t* const* fwd_rowptr,
+                              const int32_t* const* fwd_colidx, const void* const* fwd_vals,
+                              const int64_t* const* bwd_rowptr, const int32_t* const* bwd_colidx,
+                              const void* const* bwd_vals, int dtype) {
+  if (!out || N < 0 || E <= 0 || !fwd_rowptr || !fwd_colidx || !fwd_vals) return B200GF_EINVAL;
+  if (dtype != B200GF_F32 && dtype != B200GF_F64) return B200GF_EUNSUPPORTED;
+  if (N > (int64_t)INT32_MAX) return B200GF_EUNSUPPORTED;
+  *out = nullptr;
+  DeviceGuard guard;
+  b200gf_plan* p = new (std::nothrow) b200gf_plan();
+  if (!p) return B200GF_ENOMEM;
+  int rc = init_device(p, device);
+  if (rc) { delete p; return rc; }
+  p->dtype = dtype; p->n_rows = N; p->n_cols = N; p->E = E;
+  p->has_bwd = bwd_rowptr && bwd_colidx && bwd_vals;
+  p->fwd.resize(E);
+  if (p->has_bwd) p->bwd.resize(E);
+  const size_t es = dtype_size(dtype);
+  for (int e = 0; e < E && rc == B200GF_OK; ++e) {
+    if ((rc = adopt(fwd_rowptr[e], fwd_colidx[e], fwd_vals[e], N, es, p->fwd[e]))) break;
+    if (p->has_bwd && (rc = adopt(bwd_rowptr[e], bwd_colidx[e], bwd_vals[e], N, es, p->bwd[e]))) break;
+  }
+  if (rc == B200GF_OK && cudaDeviceSynchronize() != cudaSuccess) rc = B200GF_ECUDA - (int)cudaGetLastError();
+  if (rc) { b200gf_plan_destroy(p); return rc; }
+  *out = p;
+  return B200GF_OK;
+}
+
 int64_t b200gf_plan_info(const b200gf_plan* plan, int what) {
   if (!plan) return B200GF_EINVAL;
   switch (what) {

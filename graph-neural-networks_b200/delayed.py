@@ -55,6 +55,17 @@ def block_delay_csr(S):
     return out, M
 
 
+def transpose_csr_device(csr, M):
+    """CSR (rowptr, col, val) of an M x M operator -> CSR of its transpose, on the same device: one stable sort by column
+    (entries of an output row keep ascending source-row order, like the host builder's counting sort)."""
+    rowptr, col, val = csr
+    rows = torch.repeat_interleave(torch.arange(M, device=rowptr.device), rowptr[1:] - rowptr[:-1])
+    order = torch.sort(col.to(torch.int64), stable=True)[1]
+    t_rowptr = torch.zeros(M + 1, dtype=torch.int64, device=rowptr.device)
+    t_rowptr[1:] = torch.cumsum(torch.bincount(col.to(torch.int64), minlength=M), 0)
+    return t_rowptr, rows[order].to(torch.int32).contiguous(), val[order].contiguous()
+
+
 def _plan_for_batch(S):
     """Plan of the space-time operator, cached per (storage, version): GraphFilter_DB.addGSO is called once per batch
     (architecturesTime.py) and every layer of the network shares that GSO tensor."""
@@ -69,7 +80,8 @@ def _plan_for_batch(S):
     if hit is not None and hit[0]() is S:
         return hit[1]
     csr, M = block_delay_csr(S)
-    plan = Plan.from_host_csr(csr, M, S.dtype, S.device)
+    # both operators are built on the device (one sort for the transpose) and adopted device to device: no host round trip
+    plan = Plan.from_device_ops([transpose_csr_device(c, M) for c in csr], csr, M, S.dtype, S.device)
     if len(_CACHE) >= _CACHE_MAX:
         _CACHE.pop(next(iter(_CACHE)))
     _CACHE[key] = (weakref.ref(S), plan)

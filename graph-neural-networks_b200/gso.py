@@ -191,6 +191,34 @@ class Plan:
         _cabi.check(rc)
         return cls(out.value, n_rows, n_cols, len(fwd), dtype, torch.device("cuda", idx))
 
+    @classmethod
+    def from_device_ops(cls, fwd, bwd, N, dtype, device):
+        """fwd / bwd: lists (per e) of DEVICE tensors (rowptr int64 [N+1], col int32, val) — rows of S_e^T / of S_e.
+        No host round trip (b200gf_plan_create_device)."""
+        lib = _cabi.load()
+        device = torch.device(device)
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        keep = []
+
+        def pack(ops):
+            rp, ci, va = [], [], []
+            for (r, c, v) in ops:
+                r = r.to(torch.int64).contiguous(); c = c.to(torch.int32).contiguous(); v = v.to(dtype).contiguous()
+                keep.extend([r, c, v])
+                rp.append(r.data_ptr()); ci.append(c.data_ptr()); va.append(v.data_ptr())
+            return _cabi.ptr_array(rp), _cabi.ptr_array(ci), _cabi.ptr_array(va)
+
+        f = pack(fwd)
+        b = pack(bwd) if bwd is not None else (None, None, None)
+        out = ctypes.c_void_p()
+        with torch.cuda.device(idx):
+            torch.cuda.current_stream().synchronize()          # the arrays were produced on the caller's stream
+            rc = lib.b200gf_plan_create_device(ctypes.byref(out), idx, N, len(fwd), f[0], f[1], f[2], b[0], b[1], b[2],
+                                               _TORCH2ENUM[dtype])
+        _cabi.check(rc)
+        del keep
+        return cls(out.value, N, N, len(fwd), dtype, torch.device("cuda", idx))
+
     def info(self, what):
         return int(_cabi.load().b200gf_plan_info(self._h, what))
 

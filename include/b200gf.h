@@ -83,6 +83,16 @@ int b200gf_plan_create_ops(b200gf_plan** out, int device, int64_t n_rows, int64_
                            const int64_t* const* bwd_rowptr, const int32_t* const* bwd_colidx,
                            const void* const* bwd_vals, int dtype);
 
+/* Device-side variant for GSOs that change every batch (LSIGF_DB's space-time operator, graphML.py:977-1094): both
+ * operators given as DEVICE CSR arrays with valid indices (fwd = rows of S_e^T, bwd = rows of S_e, square N x N, columns
+ * ascending inside a row; bwd_* may be NULL); they are copied device to device, nothing but the nnz counts is read back
+ * by the host and nothing is validated. */
+int b200gf_plan_create_device(b200gf_plan** out, int device, int64_t N, int E,
+                              const int64_t* const* fwd_rowptr, const int32_t* const* fwd_colidx,
+                              const void* const* fwd_vals,
+                              const int64_t* const* bwd_rowptr, const int32_t* const* bwd_colidx,
+                              const void* const* bwd_vals, int dtype);
+
 void b200gf_plan_destroy(b200gf_plan* plan);
 
 /* introspection: what = 0 n_rows, 1 n_cols, 2 E, 3 dtype, 4 device, 5 nnz (sum over e, forward operator),

@@ -168,6 +168,54 @@ def test_gpu_flocking_sized_batch_against_batched_matmul():
     assert float((y32.double() - ref).abs().max() / ref.abs().max()) < 1e-4
 
 
+@pytest.mark.gpu
+def test_gpu_plan_build_stays_on_the_device():
+    """the space-time plan used to travel through the host once per GSO batch (D2H of the CSR, host
+    transpose, H2D).  Now both operators are built with torch kernels on the device and adopted device to device
+    (b200gf_plan_create_device); same results as the host builder, timing of both printed."""
+    import time
+    from gnn_b200 import delayed
+    from gnn_b200.gso import Plan
+    import gnn_b200
+    torch.manual_seed(1)
+    B, T, N, E = 20, 60, 50, 1
+    S = (torch.rand(B, T, E, N, N, device="cuda") < 0.15).float()
+    S = S / S.sum(-1, keepdim=True).clamp(min=1.0)
+    csr, M = delayed.block_delay_csr(S)
+
+    def clock(fn, reps=3):
+        fn(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps * 1e3
+
+    dev_ms = clock(lambda: Plan.from_device_ops([delayed.transpose_csr_device(c, M) for c in csr], csr, M, S.dtype, S.device))
+    host_ms = clock(lambda: Plan.from_host_csr(csr, M, S.dtype, S.device))
+    p_dev = Plan.from_device_ops([delayed.transpose_csr_device(c, M) for c in csr], csr, M, S.dtype, S.device)
+    p_host = Plan.from_host_csr(csr, M, S.dtype, S.device)
+    x = torch.randn(1, 4, M, device="cuda")
+    h = torch.randn(3, E, 3, 4, device="cuda")
+    assert torch.equal(gnn_b200.LSIGF(h, p_dev, x, None), gnn_b200.LSIGF(h, p_host, x, None))
+    print("LSIGF_DB plan for B=%d T=%d N=%d (%d space-time nodes, %d nnz): device build %.2f ms, host build %.2f ms" %
+          (B, T, N, M, p_dev.nnz, dev_ms, host_ms))
+
+
+def test_transpose_csr_device_matches_scipy():
+    import scipy.sparse as sp
+    from gnn_b200 import delayed
+    for M, seed in ((1, 0), (7, 1), (60, 2)):
+        m = sp.random(M, M, density=0.2, format="csr", random_state=seed)
+        m.sort_indices()
+        tr, tc, tv = delayed.transpose_csr_device((torch.tensor(m.indptr, dtype=torch.int64),
+                                                   torch.tensor(m.indices, dtype=torch.int32), torch.tensor(m.data)), M)
+        mt = m.T.tocsr()
+        mt.sort_indices()
+        assert np.array_equal(tr.numpy(), mt.indptr) and np.array_equal(tc.numpy(), mt.indices)
+        assert np.array_equal(tv.numpy(), mt.data)
+
+
 # ------------------------------------------------------------------------------------------------ CPU, random shapes
 from hypothesis import given, settings, strategies as st  # noqa: E402
 
