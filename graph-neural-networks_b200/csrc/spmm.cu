@@ -136,7 +136,7 @@ static int launch_v2_sc(int sm_count, const CsrDev& A, int64_t n_rows, const T* 
 template <typename T, int SCATTER>
 static int launch_multirow_v2(int sm_count, const CsrDev& A, int64_t n_rows, const T* src, int64_t src_ld, T* dst,
                               int64_t dst_ld, int C, cudaStream_t st, const ScatterHost* sh) {
-  constexpr int VEC = 32 / sizeof(T), L = 2, GS = 8, U = 2, THREADS = 256, MINB = 3, HINT = 3;
+  constexpr int VEC = 32 / sizeof(T), L = 2, GS = 8, U = 2, THREADS = 256, MINB = sizeof(T) == 4 ? 4 : 3, HINT = 3;  // fp32: 4 blocks (0.266 ms) beat 3 (0.298 ms) although ptxas parks 16 bytes of per-row-group scalars on the stack
   auto kern = spmm_hop_multirow_v2_kernel<T, int32_t, VEC, L, GS, U, THREADS, MINB, HINT, SCATTER>;
   if (n_rows == 0) return B200GF_OK;
   constexpr int rows_per_block = (THREADS / 32) * (32 / GS);
