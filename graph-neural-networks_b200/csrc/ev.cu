@@ -217,10 +217,9 @@ inline int grid_for(int64_t total) { return (int)imin64((total + 255) / 256, 148
 // 16-byte batch vectors: float data, B a multiple of 4, every operand 16-byte aligned (all row strides are multiples of B)
 template <typename T>
 inline bool vec4_ok(int B, const void* a, const void* b, const void* c, const void* d) {
-  if (sizeof(T) != 4 || B % 4 != 0) return false;
-  for (const void* p : {a, b, c, d})
-    if (p && (reinterpret_cast<uintptr_t>(p) & 15)) return false;
-  return true;
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+                         reinterpret_cast<uintptr_t>(d);
+  return sizeof(T) == 4 && B % 4 == 0 && (bits & 15) == 0;
 }
 
 template <typename T>
