@@ -643,6 +643,7 @@ def multi_gpu_selftest(ctx):
                     errs["symmetric_memory"] = next(iter(part._arenas.values())).kind
                 errs["ok"] = bool(max(errs[k] for k in ("y", "dh", "dx", "db")) < tol)
                 res[key] = errs
+            part.close()
             del part
     return res
 
@@ -706,7 +707,7 @@ def multi_gpu_arm(ctx, w, out_fd):
         mode = modes[int(pick.item())]
     for m in modes:
         if m != mode:
-            built.pop(m)
+            built.pop(m)[0].close()                              # collective: every rank drops the same sharding
             torch.cuda.empty_cache()
     part, x_local, fwd, graphed = built[mode]
     hops = E * (K - 1)

@@ -337,6 +337,18 @@ class PartitionedLSIGF:
         else:
             self.fused = bool(self._fused_req)
 
+    def close(self):
+        """Collective: release the symmetric memory of this object (arenas of the node sharding, operands of the feature
+        sharding).  Every rank must call it; nothing may be in flight on other ranks' streams (it synchronises + barriers)."""
+        for a in list(self._arenas.values()):
+            a.close()
+        self._arenas = {}
+        for sy in list(self._symm_by_width.values()):
+            sy.close()
+        self._symm_by_width = {}
+        self._symm = None
+        self._graph_keepalive = None
+
     # -- helpers -----------------------------------------------------------------------------------
     def feature_slice(self, G):
         """[g0, g1) of the in-features this rank owns in features mode."""
