@@ -58,7 +58,7 @@ __device__ __forceinline__ void bstore(T* p, const BVec<T, VB>& a) {
 }
 
 // step k of every chain (f, g, b) for one edge feature; one thread owns (f, i, VB consecutive b) and loops over g
-template <typename T, int VB>
+template <typename T, int VB, int GB = 8>
 __global__ void __launch_bounds__(256)
 step_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ diag,
             const T* __restrict__ w, const T* __restrict__ uprev, const T* __restrict__ xT, T* __restrict__ ucur,
@@ -77,27 +77,47 @@ step_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
     const T* __restrict__ wk = w + ((size_t)(f * K + k) * G) * nnz;                    // + g * nnz
     const T* __restrict__ up = (k == 0 ? xT : uprev + (size_t)f * G * plane) + b;      // + g * plane
     T* __restrict__ uc = ucur ? ucur + (size_t)f * G * plane + (size_t)i * B + b : nullptr;
-    for (int g = 0; g < G; ++g, wk += nnz, up += plane) {
-      BVec<T, VB> acc;
-      acc.zero();
+    // GB input features at a time: their loads (one weight + one state row each per non-zero) are independent, so GB
+    // requests are in flight per thread instead of one (ncu on the one-g-at-a-time loop: 88 % long-scoreboard stalls,
+    // 0.32 eligible warps per scheduler, DRAM at 26 % — profiles/r2_prof_ev_step_details.txt)
+    for (int g0 = 0; g0 < G; g0 += GB) {
+      BVec<T, VB> acc[GB];
+#pragma unroll
+      for (int q = 0; q < GB; ++q) acc[q].zero();
       if (d != -2) {
         if (d >= 0) {
-          const T wv = wk[d];
-          const BVec<T, VB> u = bload<T, VB>(up + (size_t)i * B);
 #pragma unroll
-          for (int q = 0; q < VB; ++q) acc.v[q] = wv * u.v[q];
+          for (int q = 0; q < GB; ++q) {
+            if (g0 + q < G) {
+              const T wv = wk[(size_t)(g0 + q) * nnz + d];
+              const BVec<T, VB> u = bload<T, VB>(up + (size_t)(g0 + q) * plane + (size_t)i * B);
+#pragma unroll
+              for (int r = 0; r < VB; ++r) acc[q].v[r] = wv * u.v[r];
+            }
+          }
         }
       } else {
         for (int idx = beg; idx < end; ++idx) {
-          const T wv = wk[idx];
-          const BVec<T, VB> u = bload<T, VB>(up + (size_t)col[idx] * B);
+          const size_t cb = (size_t)col[idx] * B;
 #pragma unroll
-          for (int q = 0; q < VB; ++q) acc.v[q] = fma(wv, u.v[q], acc.v[q]);
+          for (int q = 0; q < GB; ++q) {
+            if (g0 + q < G) {
+              const T wv = wk[(size_t)(g0 + q) * nnz + idx];
+              const BVec<T, VB> u = bload<T, VB>(up + (size_t)(g0 + q) * plane + cb);
+#pragma unroll
+              for (int r = 0; r < VB; ++r) acc[q].v[r] = fma(wv, u.v[r], acc[q].v[r]);
+            }
+          }
         }
       }
-      if (uc) { bstore<T, VB>(uc, acc); uc += plane; }
 #pragma unroll
-      for (int q = 0; q < VB; ++q) ysum.v[q] += acc.v[q];
+      for (int q = 0; q < GB; ++q) {
+        if (g0 + q < G) {
+          if (uc) bstore<T, VB>(uc + (size_t)(g0 + q) * plane, acc[q]);
+#pragma unroll
+          for (int r = 0; r < VB; ++r) ysum.v[r] += acc[q].v[r];
+        }
+      }
     }
     T* __restrict__ y = Y + ((size_t)f * NA + i) * B + b;
     if (k != 0) {
@@ -137,11 +157,23 @@ adjoint_step_kernel(const int64_t* __restrict__ rowptrT, const int32_t* __restri
     const T* __restrict__ lk = lam_k + (size_t)fg * NA * B + b;
     BVec<T, VB> acc = bload<T, VB>(dY + ((size_t)f * NA + j) * B + b);
     const int beg = (int)rowptrT[j], end = (int)rowptrT[j + 1];
-    for (int it = beg; it < end; ++it) {
-      const T wv = wk[perm[it]];
-      const BVec<T, VB> l = bload<T, VB>(lk + (size_t)colT[it] * B);
+    for (int it = beg; it < end; it += 4) {                  // 4 entries per pass: their index and data loads overlap
+      T wv[4];
+      BVec<T, VB> l[4];
 #pragma unroll
-      for (int q = 0; q < VB; ++q) acc.v[q] = fma(wv, l.v[q], acc.v[q]);
+      for (int u = 0; u < 4; ++u) {
+        if (it + u < end) {
+          wv[u] = wk[perm[it + u]];
+          l[u] = bload<T, VB>(lk + (size_t)colT[it + u] * B);
+        } else {
+          wv[u] = T(0);
+          l[u].zero();
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int q = 0; q < VB; ++q) acc.v[q] = fma(wv[u], l[u].v[q], acc.v[q]);
     }
     bstore<T, VB>(lam_km1 + ((size_t)fg * NA + j) * B + b, acc);
   }
