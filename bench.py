@@ -664,7 +664,9 @@ def multi_gpu_arm(ctx, w, out_fd):
     def build(mode):
         part = PartitionedLSIGF(gso, mode=mode, device=dev, fused=False if args.no_fused else None, fence=args.fence,
                                 symm_backend=args.symm, multicast=args.multicast)
-        if mode == "nodes":
+        if mode == "grid":
+            x_local = part.grid_tile(x_nm, B, G).to(dev)        # rows of my row group x features of my column group
+        elif mode == "nodes":
             xp = torch.cat((x_nm, torch.zeros(part.n_pad - N, B * G, dtype=tdt)))
             x_local = xp[part.r0:part.r1].contiguous().to(dev)
         else:
@@ -682,15 +684,53 @@ def multi_gpu_arm(ctx, w, out_fd):
         return part, x_local, fwd, graphed
 
     modes = ["nodes", "features"] if args.mode == "auto" else [args.mode]
+    vq = 8 if tdt == torch.float32 else 4
+    if args.mode == "auto" and world >= 4 and world % 2 == 0 and G % (world // 2) == 0 and (G // (world // 2)) % vq == 0 \
+            and B * (G // (world // 2)) >= 2 * vq and not args.no_fused:
+        modes.append("grid")                                     # 2-D process grid (2 row groups x world/2 column groups)
+    want = None
+    if not args.no_check and rank == 0:                          # fp64 CPU oracle at full size, once, before any timing
+        t0 = time.time()
+        want = oracle_forward_nm(gso, h_cpu, b_cpu, x_nm, B, G)
+        oracle_s = time.time() - t0
     tried = {}
-    built = {}
     tried_fb = {}
+    parity = {}
+    built = {}
     for mode in modes:
-        built[mode] = build(mode)
+        try:
+            built[mode] = build(mode)
+        except Exception as exc:                                 # a sharding that cannot be built here is skipped, loudly
+            out.setdefault("modes_skipped", {})[mode] = repr(exc)[:200]
+            ok_t = torch.tensor([0], device=dev)
+        else:
+            ok_t = torch.tensor([1], device=dev)
+        dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+        if int(ok_t.item()) == 0:
+            if mode in built:
+                built.pop(mode)[0].close()
+            out.setdefault("modes_skipped", {}).setdefault(mode, "failed on another rank")
+            continue
         with torch.no_grad():
             ms_probe, _ = ctx.timed(built[mode][2], 5, 3)
         tried[mode] = ms_probe
-        if not args.no_bwd:   # forward + the collective backward (dh, db all-reduced; dx sharded like x), per sharding
+        if not args.no_check:                                    # every probed sharding is checked; a wrong one is never timed
+            with torch.no_grad():
+                y_rows = built[mode][2]().contiguous()
+            ys = [torch.empty_like(y_rows) for _ in range(world)]
+            dist.all_gather(ys, y_rows)
+            good = torch.tensor([1], device=dev)
+            if rank == 0:
+                parity[mode] = max_rel(torch.cat(ys)[:N], want)
+                good[0] = 1 if parity[mode] < ctx.tol else 0
+            dist.broadcast(good, 0)
+            del ys
+            if int(good.item()) == 0:
+                tried.pop(mode)
+                built.pop(mode)[0].close()
+                out.setdefault("modes_skipped", {})[mode] = "parity_max_rel %.3e above tolerance" % parity.get(mode, float("nan"))
+                continue
+        if not args.no_bwd and mode != "grid":   # forward + the collective backward (dh, db all-reduced; dx sharded like x)
             part_m, x_m = built[mode][0], built[mode][1]
             dy_rows = torch.randn(part_m.rows_per_rank, B * F, generator=torch.Generator().manual_seed(100 + rank)).to(dev, tdt)
 
@@ -700,12 +740,14 @@ def multi_gpu_arm(ctx, w, out_fd):
 
             with torch.no_grad():
                 tried_fb[mode], _ = ctx.timed(fwd_bwd, max(3, args.steps // 4), 2)
+    if not tried:
+        raise SystemExit("bench.py: no multi-GPU sharding passed its parity check: %r" % out.get("modes_skipped"))
     mode = min(tried, key=tried.get)
     if len(modes) > 1:
         pick = torch.tensor([modes.index(mode)], device=dev)
         dist.broadcast(pick, 0)                                  # every rank times the same sharding
         mode = modes[int(pick.item())]
-    for m in modes:
+    for m in list(built):
         if m != mode:
             built.pop(m)[0].close()                              # collective: every rank drops the same sharding
             torch.cuda.empty_cache()
@@ -733,18 +775,17 @@ def multi_gpu_arm(ctx, w, out_fd):
             torch.cuda.synchronize()
             hop_ms = ctypes_floats(lib, part.plan, hops * 8)[hops * 3:]
             lib.b200gf_profile_hops(part.plan.handle, 0)
-    # parity of the timed path at full size: gather every rank's rows, compare with the CPU oracle on rank 0
+        dist.barrier()     # eager and replayed steps alternate the double-buffered operands independently: never overlap them
+    # parity of the TIMED path at full size, after the timed region: gather every rank's rows, compare on rank 0
     if not args.no_check:
         with torch.no_grad():
             y_rows = fwd().contiguous()
         ys = [torch.empty_like(y_rows) for _ in range(world)]
         dist.all_gather(ys, y_rows)
         if rank == 0:
-            t0 = time.time()
-            want = oracle_forward_nm(gso, h_cpu, b_cpu, x_nm, B, G)
             out["parity_max_rel"] = max_rel(torch.cat(ys)[:N], want)
-            out["parity_note"] = "all %d x %d outputs (rows gathered from %d ranks) vs the fp64 CPU oracle at full size (%.1f s on the host)" % (N, B * F, world, time.time() - t0)
-            del want
+            out["parity_note"] = "all %d x %d outputs (rows gathered from %d ranks) vs the fp64 CPU oracle at full size (%.1f s on the host)" % (N, B * F, world, oracle_s)
+            out["modes_parity"] = parity
         del ys
         dist.barrier()
     # e2e: every rank copies its shard in from pinned host memory and its result rows back
@@ -765,14 +806,17 @@ def multi_gpu_arm(ctx, w, out_fd):
         out["fwd_bwd"] = {"ms_per_step": tried_fb[best], "unit": "edge-feature-op/s",
                           "value": float(gso.nnz()) * (K - 1) * B * (G + F) / (tried_fb[best] * 1e-3),
                           "note": "partitioned forward + backward, %s sharding" % best, "modes_probed_ms": tried_fb}
-    if mode == "nodes":
+    if mode == "grid":
+        c_loc, nnz_loc, rows_loc = B * (G // part.Pc), part.local_nnz // E, part.rows_per_group
+    elif mode == "nodes":
         c_loc, nnz_loc, rows_loc = B * G, part.local_nnz // E, part.rows_per_rank
     else:
         g0, g1 = part.feature_slice(G)
         c_loc, nnz_loc, rows_loc = B * (g1 - g0), nnz_e, N
     rf = hop_roofline(ctx, hop_ms, ms * max(1, len(hop_ms) // max(hops, 1)), nnz_loc, rows_loc, c_loc,
                       "hop kernel, rank 0 shard: %d rows x %d columns, %d nnz%s" %
-                      (rows_loc, c_loc, nnz_loc, " (fused all-gather epilogue)" if mode == "nodes" and part.fused else ""))
+                      (rows_loc, c_loc, nnz_loc, " (fused all-gather epilogue)" if mode == "nodes" and part.fused else
+                       (" (all-gather + scatter epilogue)" if mode == "grid" else "")))
     out["roofline"] = rf
     out["e2e"] = {"value": ops_per_step / (ms_e2e * 1e-3), "unit": "edge-feature-op/s",
                   "h2d_bytes_per_step": xh.numel() * es * world, "d2h_bytes_per_step": yh.numel() * es * world,
@@ -780,13 +824,15 @@ def multi_gpu_arm(ctx, w, out_fd):
     out["clocks"] = clk.summary()
     out["modes_probed_ms"] = tried
     symm = None
-    if mode == "nodes" and part._arenas:
+    if mode in ("nodes", "grid") and part._arenas:
         symm = next(iter(part._arenas.values())).kind
-    parallelism = "%s-partition x%d%s%s%s" % (
-        mode, world,
-        (" (all-gather fused into the hop kernel: %s, peer-flag fences)" % symm) if (mode == "nodes" and part.fused) else
-        (" (fused hop+NVLink scatter, %s fence)" % args.fence if part.fused else " (NCCL collectives)"),
-        ", CUDA graph" if graphed else "", "")
+    if mode == "grid":
+        how = " (%d row groups x %d column groups; all-gather in the column group + scatter in the row group fused into the hop kernel: %s, peer-flag fences)" % (part.Pr, part.Pc, symm)
+    elif mode == "nodes" and part.fused:
+        how = " (all-gather fused into the hop kernel: %s, peer-flag fences)" % symm
+    else:
+        how = " (fused hop+NVLink scatter, %s fence)" % args.fence if part.fused else " (NCCL collectives)"
+    parallelism = "%s-partition x%d%s%s" % (mode, world, how, ", CUDA graph" if graphed else "")
     if not args.no_selftest:
         st = multi_gpu_selftest(ctx)
         if rank == 0:
@@ -895,9 +941,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="er1m", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="auto", choices=["auto", "nodes", "features"],
-                    help="multi-GPU sharding (DESIGN.md §4): node rows (north_star), feature columns, or probe both and "
-                         "time the faster one (default)")
+    ap.add_argument("--mode", default="auto", choices=["auto", "nodes", "features", "grid"],
+                    help="multi-GPU sharding (DESIGN.md §4): node rows (north_star), feature columns, the 2-D grid of both "
+                         "(4 / 8 GPUs), or probe all that apply, check each against the oracle and time the fastest (default)")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"], help="arithmetic type (headline: f32)")
     ap.add_argument("--configs", default="cfg2,cfg3,cfg4,cfg4ev",
                     help="N = 1: other BASELINE.json configurations measured in the same run ('' = none)")

@@ -47,6 +47,8 @@ _SIGNATURES = {
                                    c_int, c_i64, c_vp]),
     "b200gf_scatter_rows": (c_int, [c_int, c_vp, c_i64, c_i64, c_int, PP, c_int, c_i64, c_i64, c_i64, c_int, c_i64, c_vp]),
     "b200gf_hop_bcast": (c_int, [c_vp, c_int, c_int, c_vp, c_i64, c_int, PP, c_int, c_vp, c_i64, c_i64, c_vp]),
+    "b200gf_hop_grid": (c_int, [c_vp, c_int, c_int, c_vp, c_i64, c_int, PP, c_int, c_i64, c_i64, PP, c_int, c_i64, c_i64, c_i64,
+                                c_int, c_i64, c_vp]),
     "b200gf_bcast_rows": (c_int, [c_int, c_vp, c_i64, c_i64, c_int, PP, c_int, c_vp, c_i64, c_i64, c_vp]),
     "b200gf_symm_alloc": (c_int, [PP, c_sz]),
     "b200gf_symm_free": (c_int, [c_vp]),

@@ -115,6 +115,7 @@ static int launch_v2(int sm_count, const CsrDev& A, int64_t n_rows, const T* src
   ScatterParam<T, SCATTER> sp{};
   if constexpr (SCATTER == EPI_SCATTER) sp.a = make_scatter<T>(sh);
   if constexpr (SCATTER == EPI_BCAST) sp.a = make_bcast<T>(bh);
+  if constexpr (SCATTER == EPI_GRID) { sp.s = make_scatter<T>(sh); sp.a = make_bcast<T>(bh); }
   kern<<<dim3((unsigned)blocks, (unsigned)n_chunks), THREADS, 0, st>>>(A.rowptr32, A.col, reinterpret_cast<const T*>(A.val),
                                                                       src, (int)src_ld, dst, (int)dst_ld, (int)n_rows, C,
                                                                       B200GF_HOP_L2_FRAC, sp);
@@ -125,6 +126,7 @@ static int launch_v2(int sm_count, const CsrDev& A, int64_t n_rows, const T* src
 template <typename T, int L>
 static int launch_v2_sc(int sm_count, const CsrDev& A, int64_t n_rows, const T* src, int64_t src_ld, T* dst,
                         int64_t dst_ld, int C, cudaStream_t st, const ScatterHost* sh, const BcastHost* bh) {
+  if (bh && sh) return launch_v2<T, L, EPI_GRID>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh, bh);
   if (bh) return launch_v2<T, L, EPI_BCAST>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, nullptr, bh);
   if (sh && sh->n_peers > 0) return launch_v2<T, L, EPI_SCATTER>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh, nullptr);
   return launch_v2<T, L, EPI_NONE>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, nullptr, nullptr);
@@ -135,7 +137,7 @@ static int launch_v2_sc(int sm_count, const CsrDev& A, int64_t n_rows, const T* 
 // at C = 8 the 32-byte lanes bring nothing (0.20 vs 0.19 ms), those rows stay on spmm_hop_multirow_kernel.
 template <typename T, int SCATTER>
 static int launch_multirow_v2(int sm_count, const CsrDev& A, int64_t n_rows, const T* src, int64_t src_ld, T* dst,
-                              int64_t dst_ld, int C, cudaStream_t st, const ScatterHost* sh) {
+                              int64_t dst_ld, int C, cudaStream_t st, const ScatterHost* sh, const BcastHost* bh = nullptr) {
   constexpr int VEC = 32 / sizeof(T), L = 2, GS = 8, U = 2, THREADS = 256, MINB = sizeof(T) == 4 ? 4 : 3, HINT = 3;  // fp32: 4 blocks (0.266 ms) beat 3 (0.298 ms) although ptxas parks 16 bytes of per-row-group scalars on the stack
   auto kern = spmm_hop_multirow_v2_kernel<T, int32_t, VEC, L, GS, U, THREADS, MINB, HINT, SCATTER>;
   if (n_rows == 0) return B200GF_OK;
@@ -148,6 +150,7 @@ static int launch_multirow_v2(int sm_count, const CsrDev& A, int64_t n_rows, con
   if (blocks > cap) blocks = cap;
   ScatterParam<T, SCATTER> sp{};
   if constexpr (SCATTER == EPI_SCATTER) sp.a = make_scatter<T>(sh);
+  if constexpr (SCATTER == EPI_GRID) { sp.s = make_scatter<T>(sh); sp.a = make_bcast<T>(bh); }
   kern<<<(unsigned)blocks, THREADS, 0, st>>>(A.rowptr32, A.col, reinterpret_cast<const T*>(A.val), src, (int)src_ld, dst,
                                              (int)dst_ld, (int)n_rows, C, sp);
   LAUNCH_CHECK();
@@ -161,18 +164,29 @@ static int launch_typed(int sm_count, const CsrDev& A, int64_t n_rows, const voi
   const T* src = reinterpret_cast<const T*>(src_);
   T* dst = reinterpret_cast<T*>(dst_);
   if (bh) {
-    // fused all-gather epilogue: only the v2 kernel has it (32-byte aligned rows on both sides, 32-bit offsets)
+    // fused all-gather epilogue (EPI_BCAST), or all-gather + scatter (EPI_GRID, when `sh` is given too): v2 kernels only
+    // (32-byte aligned rows on every side, 32-bit offsets, rows of at least 64 bytes)
     constexpr int VWb = 32 / sizeof(T);
     const int Cwb = (C + VWb - 1) / VWb * VWb;
-    bool ok = A.rowptr32 != nullptr && src_ld % VWb == 0 && Cwb <= src_ld && Cwb <= bh->out_ld && bh->out_ld % VWb == 0 &&
-              (reinterpret_cast<uintptr_t>(src) & 31) == 0 && src_ld <= INT32_MAX && n_rows <= INT32_MAX;
+    const bool grid = sh && sh->n_peers > 0;
+    bool ok = A.rowptr32 != nullptr && src_ld % VWb == 0 && Cwb <= src_ld && (reinterpret_cast<uintptr_t>(src) & 31) == 0 &&
+              src_ld <= INT32_MAX && n_rows <= INT32_MAX && Cwb >= 2 * VWb;
+    if (bh->n_peers > 0) ok = ok && Cwb <= bh->out_ld && bh->out_ld % VWb == 0;
     for (int i = 0; i < bh->n_peers; ++i) ok = ok && (reinterpret_cast<uintptr_t>(bh->peer[i]) & 31) == 0;
     ok = ok && (reinterpret_cast<uintptr_t>(bh->mc) & 31) == 0;
+    if (grid) ok = ok && sh->gl % VWb == 0 && sh->out_ld % VWb == 0 && sh->out_col % VWb == 0 && sh->stride_b % VWb == 0;
+    if (!grid && bh->n_peers <= 0) ok = false;
+    if (dst_) ok = ok && dst_ld % VWb == 0 && Cwb <= dst_ld && (reinterpret_cast<uintptr_t>(dst_) & 31) == 0 && dst_ld <= INT32_MAX;
     if (!ok) return B200GF_EUNSUPPORTED;
     const int nwb = Cwb / VWb;
-    if (nwb <= 8) return launch_v2_sc<T, 8>(sm_count, A, n_rows, src, src_ld, nullptr, 0, C, st, nullptr, bh);
-    if (nwb <= 16) return launch_v2_sc<T, 16>(sm_count, A, n_rows, src, src_ld, nullptr, 0, C, st, nullptr, bh);
-    return launch_v2_sc<T, 32>(sm_count, A, n_rows, src, src_ld, nullptr, 0, C, st, nullptr, bh);
+    if (nwb == 2) {
+      if (!grid) return B200GF_EUNSUPPORTED;        // 64-byte rows: only the grid epilogue is instantiated for the multi-row kernel
+      return launch_multirow_v2<T, EPI_GRID>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh, bh);
+    }
+    if (nwb <= 4) return launch_v2_sc<T, 4>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, grid ? sh : nullptr, bh);
+    if (nwb <= 8) return launch_v2_sc<T, 8>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, grid ? sh : nullptr, bh);
+    if (nwb <= 16) return launch_v2_sc<T, 16>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, grid ? sh : nullptr, bh);
+    return launch_v2_sc<T, 32>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, grid ? sh : nullptr, bh);
   }
   const int Cv = (C + VEC - 1) / VEC * VEC;
   const bool vec_ok = (src_ld % VEC == 0) && (dst_ld % VEC == 0) && (Cv <= src_ld) && (Cv <= dst_ld) &&
@@ -224,7 +238,8 @@ int launch_hop(int dtype, int sm_count, const CsrDev& A, int64_t n_rows, const v
                void* dst, int64_t dst_ld, int C, cudaStream_t st, const ScatterHost* sh, const BcastHost* bh) {
   if (C <= 0 || src_ld < C || (!bh && dst_ld < C)) return B200GF_EINVAL;
   if (sh && (sh->n_peers < 0 || sh->n_peers > MAX_PEERS)) return B200GF_EINVAL;
-  if (bh && (bh->n_peers <= 0 || bh->n_peers > MAX_PEERS || bh->out_ld < C || sh)) return B200GF_EINVAL;
+  if (bh && (bh->n_peers < 0 || bh->n_peers > MAX_PEERS || (bh->n_peers > 0 && bh->out_ld < C))) return B200GF_EINVAL;
+  if (bh && bh->n_peers == 0 && !(sh && sh->n_peers > 0)) return B200GF_EINVAL;   // no all-gather only in the grid epilogue
   if (dtype == B200GF_F32) return launch_typed<float>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh, bh);
   if (dtype == B200GF_F64) return launch_typed<double>(sm_count, A, n_rows, src, src_ld, dst, dst_ld, C, st, sh, bh);
   return B200GF_EUNSUPPORTED;
@@ -367,6 +382,28 @@ extern "C" int b200gf_hop_bcast(const b200gf_plan* plan, int e, int direction, c
   if (rc) return rc;
   const b200gf::CsrDev& A = direction == B200GF_HOP_FWD ? plan->fwd[e] : plan->bwd[e];
   return b200gf::plan_hop(plan, A, src, src_ld, nullptr, 0, C, (cudaStream_t)stream, nullptr, &bh);
+}
+
+extern "C" int b200gf_hop_grid(const b200gf_plan* plan, int e, int direction, const void* src, int64_t src_ld, int C,
+                               const void* const* bc_peers, int n_bc, int64_t row0, int64_t bc_ld,
+                               const void* const* sc_peers, int n_sc, int64_t rows_per_peer, int64_t out_ld, int64_t out_col,
+                               int gl, int64_t stride_b, void* stream) {
+  if (!plan || !src || e < 0 || e >= plan->E) return B200GF_EINVAL;
+  if (direction != B200GF_HOP_FWD && direction != B200GF_HOP_BWD) return B200GF_EINVAL;
+  if (direction == B200GF_HOP_BWD && !plan->has_bwd) return B200GF_EINVAL;
+  b200gf::BcastHost bh{};
+  if (n_bc > 0) {
+    int rc = fill_bcast(bh, bc_peers, n_bc, nullptr, row0, bc_ld);
+    if (rc) return rc;
+  } else {
+    bh.n_peers = 0; bh.mc = nullptr; bh.row0 = 0; bh.out_ld = 0;
+  }
+  b200gf::ScatterHost sh{};
+  int rc = fill_scatter(sh, sc_peers, n_sc, rows_per_peer, out_ld, out_col, gl, stride_b);
+  if (rc) return rc;
+  if (plan->n_rows > rows_per_peer * n_sc || C % gl != 0) return B200GF_EINVAL;
+  const b200gf::CsrDev& A = direction == B200GF_HOP_FWD ? plan->fwd[e] : plan->bwd[e];
+  return b200gf::plan_hop(plan, A, src, src_ld, nullptr, 0, C, (cudaStream_t)stream, &sh, &bh);
 }
 
 extern "C" int b200gf_bcast_rows(int dtype, const void* src, int64_t src_ld, int64_t n_rows, int C,

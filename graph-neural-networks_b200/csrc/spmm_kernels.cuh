@@ -327,13 +327,35 @@ __device__ __forceinline__ void bcast_store(const BcastArgs<T>& bc, int64_t row,
 }
 
 // epilogue of the v2 / async kernels.  MODE 0: plain hop; 1: feature-sharded scatter (ScatterArgs); 2: row broadcast.
-constexpr int EPI_NONE = 0, EPI_SCATTER = 1, EPI_BCAST = 2;
+//                               3 (2-D process grid): both — the row is all-gathered inside the rank's column group AND its
+//                               slice is delivered to the row's contraction owner inside the rank's row group.
+constexpr int EPI_NONE = 0, EPI_SCATTER = 1, EPI_BCAST = 2, EPI_GRID = 3;
 template <typename T, int MODE>
 struct ScatterParam {};
 template <typename T>
 struct ScatterParam<T, EPI_SCATTER> { ScatterArgs<T> a; };
 template <typename T>
 struct ScatterParam<T, EPI_BCAST> { BcastArgs<T> a; };
+template <typename T>
+struct ScatterParam<T, EPI_GRID> { ScatterArgs<T> s; BcastArgs<T> a; };
+
+// shared epilogue of the v2 kernels
+template <typename T, int VEC, int MODE, int SH>
+__device__ __forceinline__ void hop_epilogue(const ScatterParam<T, MODE>& sp, T* __restrict__ dst, int dst_ld, int row, int cbase,
+                                             const Acc<T, VEC>& acc) {
+  if constexpr (MODE == EPI_BCAST) {
+    bcast_store<T, VEC>(sp.a, row, cbase, acc);              // the rank's own copy is one of the destinations
+  } else if constexpr (MODE == EPI_GRID) {
+    if (sp.a.n_peers > 0) bcast_store<T, VEC>(sp.a, row, cbase, acc);   // n_peers == 0: last hop of a chain, no all-gather
+    else if (dst != nullptr) store_vec<T, VEC, SH>(dst + (int64_t)row * dst_ld + cbase, acc);
+    scatter_store<T, VEC>(sp.s, row, cbase, acc);
+  } else {
+    store_vec<T, VEC, SH>(dst + (int64_t)row * dst_ld + cbase, acc);
+    if constexpr (MODE == EPI_SCATTER) {
+      if (sp.a.n_peers > 0) scatter_store<T, VEC>(sp.a, row, cbase, acc);
+    }
+  }
+}
 
 // HINT: 0/1 no L2 policy; 3 evict_last on every gathered line; 2 evict_last on the fraction l2_frac of the lines (by
 // address hash), the rest unchanged; 6 the same with evict_first on the rest.  SH = 1: streaming stores of the result.
@@ -398,16 +420,7 @@ spmm_hop_v2_kernel(const IDX* __restrict__ rowptr, const int32_t* __restrict__ c
       unsigned ln, gdx;
       asm volatile("mov.u32 %0, %%laneid;" : "=r"(ln));
       asm volatile("mov.u32 %0, %%nctaid.x;" : "=r"(gdx));
-      if (ln < (unsigned)L && cbase < C) {
-        if constexpr (SCATTER == EPI_BCAST) {
-          bcast_store<T, VEC>(sp.a, row, cbase, acc);        // the rank's own copy is one of the destinations
-        } else {
-          store_vec<T, VEC, SH>(dst + (int64_t)row * dst_ld + cbase, acc);
-          if constexpr (SCATTER == EPI_SCATTER) {
-            if (sp.a.n_peers > 0) scatter_store<T, VEC>(sp.a, row, cbase, acc);
-          }
-        }
-      }
+      if (ln < (unsigned)L && cbase < C) hop_epilogue<T, VEC, SCATTER, SH>(sp, dst, dst_ld, row, cbase, acc);
       row += (int)gdx * (THREADS >> 5);
     }
   }
@@ -475,16 +488,7 @@ spmm_hop_multirow_v2_kernel(const IDX* __restrict__ rowptr, const int32_t* __res
 #pragma unroll
       for (int i = 0; i < VEC; ++i) acc.v[i] += __shfl_xor_sync(FULL, acc.v[i], off);
     }
-    if (sub == 0 && col_ok && row_ok) {
-      if constexpr (SCATTER == EPI_BCAST) {
-        bcast_store<T, VEC>(sp.a, row, cbase, acc);
-      } else {
-        store_vec<T, VEC, 0>(dst + (int64_t)row * dst_ld + cbase, acc);
-        if constexpr (SCATTER == EPI_SCATTER) {
-          if (sp.a.n_peers > 0) scatter_store<T, VEC>(sp.a, row, cbase, acc);
-        }
-      }
-    }
+    if (sub == 0 && col_ok && row_ok) hop_epilogue<T, VEC, SCATTER, 0>(sp, dst, dst_ld, row, cbase, acc);
   }
 }
 

@@ -14,6 +14,12 @@ Two shardings of  y = sum_{e,k} (x S_e^k) h_{e,k} + b :
                    call (output sharded by node rows).  The right choice whenever S fits on each GPU (SURVEY §8e
                    "column split"); a reduce-scatter variant covers G not divisible by the world size.
 
+  mode="grid"      2-D process grid P = P_r x P_c (CUDA only): rank (r, c) shifts the rows of row group r for the columns of
+                   column group c.  Each hop all-gathers its rows inside the column group (P_r ranks, N*C/P_c elements
+                   instead of N*C) and delivers its slice to the contraction owner inside the row group — both from the
+                   kernel's epilogue (b200gf_hop_grid).  The all-gather that bounds the node sharding at 8 GPUs and the
+                   replicated index work that bounds the feature sharding are both cut by the grid factors.
+
 The arithmetic goes through `ops` (the C-ABI building blocks b200gf_hop / b200gf_tap_contract on CUDA).  The
 world_size-2 gloo tests inject an oracle-backed `ops` to exercise the partitioning / collective choreography on CPU;
 the product default has no CPU path.
@@ -50,6 +56,13 @@ def transpose_csr(csr, N):
     return m.indptr.astype(np.int64), m.indices.astype(np.int32), m.data
 
 
+def default_grid(world):
+    """(P_r, P_c) for the 2-D sharding: two row groups, the rest column groups (8 -> 2 x 4, 4 -> 2 x 2)."""
+    if world >= 4 and world % 2 == 0:
+        return 2, world // 2
+    return world, 1
+
+
 class CudaOps:
     """Building blocks on the GPU through the C ABI (include/b200gf.h)."""
 
@@ -83,6 +96,12 @@ class CudaOps:
     def hop_bcast(self, plan, e, direction, src, C, peers, mc, row0, out_ld):
         _cabi.check(self.lib.b200gf_hop_bcast(plan.handle, e, direction, src.data_ptr(), src.stride(0), C,
                                               _cabi.ptr_array(peers), len(peers), mc or None, row0, out_ld, self._st()))
+
+    def hop_grid(self, plan, e, direction, src, C, bc_peers, row0, bc_ld, sc_peers, rows_per_peer, out_ld, out_col, gl, stride_b):
+        _cabi.check(self.lib.b200gf_hop_grid(plan.handle, e, direction, src.data_ptr(), src.stride(0), C,
+                                             _cabi.ptr_array(bc_peers) if bc_peers else None, len(bc_peers), row0, bc_ld,
+                                             _cabi.ptr_array(sc_peers), len(sc_peers), rows_per_peer, out_ld, out_col, gl,
+                                             stride_b, self._st()))
 
     def bcast_rows(self, src, n_rows, C, peers, mc, row0, out_ld):
         _cabi.check(self.lib.b200gf_bcast_rows(_ENUM[src.dtype], src.data_ptr(), src.stride(0), n_rows, C,
@@ -293,8 +312,8 @@ class PartitionedLSIGF:
     """
 
     def __init__(self, gso, mode="nodes", group=None, device=None, ops=None, fused=None, fence="flags", symm_backend="auto",
-                 multicast=False):
-        assert mode in ("nodes", "features") and fence in ("flags", "nccl")
+                 multicast=False, grid=None):
+        assert mode in ("nodes", "features", "grid") and fence in ("flags", "nccl")
         self.mode = mode
         self.symm_backend = symm_backend   # "auto": torch symmetric memory, else CUDA IPC; "ipc"; "torch"
         # all-gather epilogue: one multimem.st through the NVSwitch multicast address instead of P peer stores.  Off by
@@ -320,7 +339,17 @@ class PartitionedLSIGF:
         self.n_pad = self.rows_per_rank * P
         self.r0 = self.rank * self.rows_per_rank
         self.r1 = self.r0 + self.rows_per_rank
-        if mode == "nodes":
+        if mode == "grid":
+            self.Pr, self.Pc = grid if grid is not None else default_grid(P)
+            assert self.Pr * self.Pc == P and self.Pr >= 1 and self.Pc >= 1, "grid must factor the world size"
+            self.rg, self.cg = self.rank // self.Pc, self.rank % self.Pc          # my row group, my column group
+            self.rows_per_group = self.rows_per_rank * self.Pc                    # rows my row group shifts per hop
+            g0, g1 = self.rg * self.rows_per_group, (self.rg + 1) * self.rows_per_group
+            fwd = [row_slice(transpose_csr(gso.csr[e], self.N), g0, g1) for e in range(self.E)]
+            self.local_nnz = int(sum(f[0][-1] for f in fwd))
+            self.plan = self.ops.make_plan_ops(fwd, None, self.rows_per_group, self.n_pad, self.dtype)
+            self._grid_step = 0
+        elif mode == "nodes":
             fwd, bwd = [], []
             for e in range(self.E):
                 st = transpose_csr(gso.csr[e], self.N)
@@ -334,6 +363,8 @@ class PartitionedLSIGF:
         self._bufs = {}
         if self._fused_req is None:
             self.fused = (ops is None and dist.get_backend(group) == "nccl" and self.world <= 16)
+        if mode == "grid" and not self.fused:
+            raise RuntimeError("b200gf: the grid sharding exists only as the fused CUDA path (NCCL process group, <= 16 ranks)")
         else:
             self.fused = bool(self._fused_req)
 
@@ -366,6 +397,8 @@ class PartitionedLSIGF:
     # -- forward -----------------------------------------------------------------------------------
     def forward(self, h, x_local, b=None, B=1):
         """B (batch size) is only read in features mode, where it cannot be inferred from an empty column slice."""
+        if self.mode == "grid":
+            return self._forward_grid(h, x_local, b, B)
         if self.mode == "nodes":
             if self.fused and self._nodes_fused_ok(x_local.shape[1]):
                 return self._forward_nodes_fused(h, x_local, b)
@@ -493,6 +526,80 @@ class PartitionedLSIGF:
         self.ops.tap_contract(vs, self.ops.pack_taps(h, True), None, dx, R, B, F, G)
         return dh, dx[:, :C], (self._bias_grad(dy_rows, B, F) if want_db else None)
 
+    # -- 2-D process grid --------------------------------------------------------------------------------
+    def grid_tile(self, x_nm, B, G):
+        """This rank's input tile of a node-major x [N, B*G]: rows of its row group (zero-padded), features of its column
+        group -> [rows_per_group, B*(G/P_c)] (column b*(G/P_c) + g)."""
+        Gl = G // self.Pc
+        xp = torch.cat((x_nm, torch.zeros(self.n_pad - x_nm.shape[0], B * G, dtype=x_nm.dtype, device=x_nm.device)))
+        r0 = self.rg * self.rows_per_group
+        return xp[r0:r0 + self.rows_per_group].view(self.rows_per_group, B, G)[:, :, self.cg * Gl:(self.cg + 1) * Gl] \
+            .reshape(self.rows_per_group, B * Gl).contiguous()
+
+    def _forward_grid(self, h, x_tile, b, B):
+        """forward(h, x_tile, b, B): x_tile from grid_tile() -> y rows [rows_per_rank, B*F] of global nodes
+        [rank*rows_per_rank, ...), like the other shardings.  Per hop: b200gf_hop_grid (all-gather inside the column group +
+        scatter inside the row group, both in the kernel's epilogue), then a peer-flag fence; the contraction operand is
+        double-buffered across steps exactly like the feature sharding's."""
+        F, E, K, G = h.shape
+        Pr, Pc = self.Pr, self.Pc
+        assert E == self.E and G % Pc == 0
+        Gl = G // Pc
+        Cl = B * Gl
+        q = 8 if self.dtype == torch.float32 else 4
+        if Gl % q != 0 or Cl < 2 * q:
+            raise RuntimeError("b200gf: grid sharding needs G / P_c a multiple of %d columns (32-byte lanes) and rows of at "
+                               "least 64 bytes; got G = %d, P_c = %d, B = %d" % (q, G, Pc, B))
+        Rc, Rr = self.rows_per_rank, self.rows_per_group
+        assert x_tile.shape[0] == Rr and x_tile.shape[1] == Cl
+        T = 1 + E * (K - 1)
+        ld = _pad_ld(Cl, self.dtype)
+        es = x_tile.element_size()
+        row_elems = B * T * G
+        key = ("grid", ld, T, row_elems)
+        ar = self._arenas.get(key)
+        if ar is None:
+            buf = (self.n_pad * ld * es + 255) // 256 * 256
+            opb = (Rc * row_elems * es + 255) // 256 * 256
+            ar = SymmetricArena(self.ops.lib, T * buf + 2 * opb, self.group, self.device, prefer=self.symm_backend)
+            ar.buf_bytes, ar.op_bytes, ar.op_off = buf, opb, T * buf
+            self._arenas[key] = ar
+        pbuf = self._grid_step & 1
+        self._grid_step += 1
+        col_group = [r * Pc + self.cg for r in range(Pr)]          # ranks holding the same feature columns
+        row_group = [self.rg * Pc + c for c in range(Pc)]          # ranks sharing my rows: the contraction owners
+        bc = lambda t: [ar.peers[p] + t * ar.buf_bytes for p in col_group]                     # noqa: E731
+        sc = [ar.peers[p] + ar.op_off + pbuf * ar.op_bytes for p in row_group]
+        row0 = self.rg * Rr
+        g0 = self.cg * Gl
+        st = self.ops._st()
+        if x_tile.stride(1) != 1 or (x_tile.stride(0) * es) % 32 or x_tile.data_ptr() % 32:
+            xt = self._buffers(("gx", Cl), (Rr, ld))
+            xt[:, :Cl].copy_(x_tile)
+            x_tile = xt
+        local_full = lambda t: ar.local(t * ar.buf_bytes, ld)                                  # noqa: E731
+        if K > 1:
+            self.ops.bcast_rows(x_tile, Rr, Cl, bc(0), 0, row0, ld)                            # z_0 for my column group
+        self.ops.scatter_rows(x_tile, Rr, Cl, sc, Rc, row_elems, g0, Gl, T * G)                # k = 0 slices to their owners
+        ar.fence(st)
+        for e in range(E):
+            src = local_full(0)
+            for k in range(1, K):
+                t = 1 + e * (K - 1) + (k - 1)
+                last = k == K - 1
+                self.ops.hop_grid(self.plan, e, _cabi.HOP_FWD, src, Cl, [] if last else bc(t), row0, ld, sc, Rc, row_elems,
+                                  t * G + g0, Gl, T * G)
+                ar.fence(st)
+                src = local_full(t)
+        W = self.ops.pack_taps(h, False).reshape(1, T * G, F)
+        y = torch.empty((Rc, _pad_ld(B * F, self.dtype)), dtype=self.dtype, device=self.device)
+        bias = None
+        if b is not None:
+            assert b.shape[1] == 1, "per-node bias is not supported by the partitioned path"
+            bias = b.contiguous()
+        self.ops.tap_contract([ar.local(ar.op_off + pbuf * ar.op_bytes, row_elems)], W, bias, y, Rc, B, T * G, F)
+        return y[:, :B * F]
+
     def _forward_features(self, h, x_cols, b, B):
         """Column-sharded hops (no communication inside a hop) + an all-to-all of every shifted slice to the rank that
         owns the node rows, overlapped with the following hops; then ONE row-local contraction over all E*K*G inputs.
@@ -595,6 +702,9 @@ class PartitionedLSIGF:
         ranks (identical everywhere), dx_local stays sharded.  SURVEY.md §8 a-8 / §8e: the K-1 shifts of dY use the
         other operator (rows of S_e), exchanged like the forward's; dh and db end in one small all-reduce."""
         assert dy_rows.shape[0] == self.rows_per_rank
+        if self.mode == "grid":
+            raise NotImplementedError("b200gf: the 2-D grid sharding has a forward only; train with mode='nodes' (fused "
+                                      "backward) or mode='features'")
         if self.mode == "nodes":
             if self.fused and self._nodes_fused_ok(x_local.shape[1]) and self._nodes_fused_ok(dy_rows.shape[1]):
                 return self._backward_nodes_fused(h, x_local, dy_rows, want_db)
@@ -725,6 +835,8 @@ class PartitionedLSIGF:
         for _ in range(2):
             self.forward(h, x_static, b, B)
         torch.cuda.synchronize()
+        if self.mode == "grid":
+            assert self._grid_step % 2 == 0
         if self.mode == "features":
             if self._symm is None:
                 raise RuntimeError("b200gf: graphed() needs the fused path (G/world a multiple of the 16-byte vector width)")

@@ -206,6 +206,19 @@ int b200gf_bcast_rows(int dtype, const void* src, int64_t src_ld, int64_t n_rows
                       const void* const* peers, int n_peers, const void* mc,
                       int64_t row0, int64_t out_ld, void* stream);
 
+/* 2-D process grid (P = P_r row groups x P_c column groups): one hop with BOTH epilogues.  The plan holds the rows of the
+ * rank's row group; src / the all-gather destinations hold only the rank's column group (C = B * G / P_c columns).  Every
+ * computed row is (a) written to row row0 + r of the full-height matrix [., bc_ld] of the n_bc ranks of the same COLUMN
+ * group (bc_peers; n_bc = 0 for the last hop of a chain: no successor needs it) and (b) delivered to the contraction
+ * operand of the rank of the same ROW group that owns node row r (sc_peers[r / rows_per_peer], local row
+ * r % rows_per_peer, column b*stride_b + out_col + g — as in b200gf_hop_scatter).  Rows of at least 64 bytes, 32-byte
+ * aligned everywhere. */
+int b200gf_hop_grid(const b200gf_plan* plan, int e, int direction,
+                    const void* src, int64_t src_ld, int C,
+                    const void* const* bc_peers, int n_bc, int64_t row0, int64_t bc_ld,
+                    const void* const* sc_peers, int n_sc, int64_t rows_per_peer,
+                    int64_t out_ld, int64_t out_col, int gl, int64_t stride_b, void* stream);
+
 /* Symmetric buffers for the above: device memory that other processes of the same node can map (CUDA IPC).
  * alloc zero-fills; export writes a 64-byte handle to send to the peers (torch.distributed); import maps a peer's
  * handle and enables peer access; close unmaps. */

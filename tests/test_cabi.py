@@ -366,3 +366,59 @@ def test_launch_counter_counts_library_kernels():
     gnn_b200.LSIGF(h, gso, x, None)
     # transpose to node-major, 3 hops, tap packing, contraction
     assert lib.b200gf_launch_count(0) == 6 and lib.b200gf_launch_count(1) == 6 and lib.b200gf_launch_count(0) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("Gl", [8, 16, 40])
+def test_grid_epilogue_on_one_gpu(Gl, dtype):
+    """b200gf_hop_grid (2-D process grid) on ONE GPU with local buffers as the peers: rows of one row group, columns of one
+    column group; every row must land (a) in all all-gather destinations at row0 + r and (b) in the contraction operand of
+    its owner at [r % rows_per_peer, b*stride_b + out_col + g]; n_bc = 0 (last hop) must only scatter.
+    Gl*B*4 bytes = 64 (multi-row kernel), 128 (L = 4) and 320 (L = 16) byte rows in fp32."""
+    import scipy.sparse as sp
+    import gnn_b200
+    from gnn_b200.gso import Plan
+    from gnn_b200.distributed import row_slice, transpose_csr
+    cabi = gnn_b200._cabi
+    lib = cabi.load()
+    if dtype == torch.float64 and Gl == 8:
+        Gl = 12                                                     # keep fp64 rows at >= 64 bytes and 32-byte lanes whole
+    N, Rr, Rc, B, T, G = 1200, 600, 200, 2, 3, 3 * Gl               # 2 row groups, 3 owners per row group
+    m = sp.random(N, N, density=0.02, format="csr", random_state=Gl)
+    m.sort_indices()
+    npd = np.float32 if dtype == torch.float32 else np.float64
+    csr = (m.indptr.astype(np.int64), m.indices.astype(np.int32), m.data.astype(npd))
+    st_csr = transpose_csr(csr, N)
+    Cl = B * Gl
+    ld = gnn_b200.padded_ld(Cl, dtype)
+    X = torch.randn(N, Cl, dtype=dtype, device="cuda")
+    src = torch.zeros(N, ld, dtype=dtype, device="cuda"); src[:, :Cl] = X
+    mr = sp.csr_matrix((m.data.astype(npd).astype(np.float64), m.indices, m.indptr), shape=m.shape)
+    ref = torch.tensor(mr.T @ X.double().cpu().numpy())
+    tol = 1e-5 if dtype == torch.float32 else 1e-13
+    stream = torch.cuda.current_stream().cuda_stream
+    row_elems = B * T * G
+    t, g0 = 2, Gl                                                    # term 2, second column group
+    for rg in range(2):
+        plan = Plan.from_ops([row_slice(st_csr, rg * Rr, (rg + 1) * Rr)], None, Rr, N, dtype, "cuda")
+        for n_bc in (2, 0):
+            gathers = [torch.full((N, ld), float("nan"), dtype=dtype, device="cuda") for _ in range(2)]
+            ops = [torch.zeros(Rc, row_elems, dtype=dtype, device="cuda") for _ in range(3)]
+            rc = lib.b200gf_hop_grid(plan.handle, 0, cabi.HOP_FWD, src.data_ptr(), ld, Cl,
+                                     cabi.ptr_array([g.data_ptr() for g in gathers]) if n_bc else None, n_bc, rg * Rr, ld,
+                                     cabi.ptr_array([o.data_ptr() for o in ops]), 3, Rc, row_elems, t * G + g0, Gl, T * G, stream)
+            assert rc == 0, lib.b200gf_strerror(rc)
+            want = ref[rg * Rr:(rg + 1) * Rr]
+            got = torch.cat(ops).view(Rr, B, T, G)[:, :, t, g0:g0 + Gl].reshape(Rr, Cl)
+            assert _rel(got.cpu().numpy(), want.numpy()) < tol
+            rest = torch.cat(ops).view(Rr, B, T, G).clone()
+            rest[:, :, t, g0:g0 + Gl] = 0
+            assert float(rest.abs().max()) == 0.0
+            for gth in gathers:
+                if n_bc:
+                    assert _rel(gth[rg * Rr:(rg + 1) * Rr, :Cl].cpu().numpy(), want.numpy()) < tol
+                    other = torch.cat((gth[:rg * Rr], gth[(rg + 1) * Rr:]))
+                    assert bool(torch.isnan(other).all())                        # only this row group's rows were written
+                else:
+                    assert bool(torch.isnan(gth).all())
