@@ -80,7 +80,7 @@ def _case(N=203, B=2, G=6, F=8, K=4, E=2, seed=3):
     return mats, x, h, b
 
 
-def _worker(rank, world, port, backend, mode, dtype_name, result_q, G=6, backward=True, F=8):
+def _worker(rank, world, port, backend, mode, dtype_name, result_q, G=6, backward=True, F=8, grid=None):
     import gnn_b200
     from gnn_b200.distributed import PartitionedLSIGF
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -100,12 +100,14 @@ def _worker(rank, world, port, backend, mode, dtype_name, result_q, G=6, backwar
         B, G, N = x.shape
         F = h.shape[0]
         gso = gnn_b200.SparseGSO.from_scipy(mats, dtype=dtype)
-        part = PartitionedLSIGF(gso, mode=mode, device=dev, ops=ops)
+        part = PartitionedLSIGF(gso, mode=mode, device=dev, ops=ops, grid=grid)
         R = part.rows_per_rank
         xn = torch.tensor(x, dtype=dtype).reshape(B * G, N).t().contiguous()       # node-major [N, B*G]
         ht = torch.tensor(h, dtype=dtype, device=dev)
         bt = torch.tensor(b, dtype=dtype, device=dev)
-        if mode == "nodes":
+        if mode == "grid":
+            x_local = part.grid_tile(xn, B, G).to(dev)
+        elif mode == "nodes":
             xp = torch.zeros(part.n_pad, B * G, dtype=dtype)
             xp[:N] = xn
             x_local = xp[part.r0:part.r1].to(dev)
@@ -163,10 +165,10 @@ def _worker(rank, world, port, backend, mode, dtype_name, result_q, G=6, backwar
         dist.destroy_process_group()
 
 
-def _run(backend, mode, dtype_name, world=2, G=6, backward=True, F=8):
+def _run(backend, mode, dtype_name, world=2, G=6, backward=True, F=8, grid=None):
     ctx = mp.get_context("spawn")
     q = ctx.SimpleQueue()
-    mp.spawn(_worker, args=(world, _free_port(), backend, mode, dtype_name, q, G, backward, F), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), backend, mode, dtype_name, q, G, backward, F, grid), nprocs=world, join=True)
     return q.get()
 
 
@@ -202,6 +204,19 @@ def test_partitioned_nccl_world2(mode, G, dtype_name, tol):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     err = _run("nccl", mode, dtype_name, G=G, backward=False)    # backward over NCCL: tests/test_widen_distributed.py
+    assert err < tol, err
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("grid", [(2, 1), (1, 2)])
+@pytest.mark.parametrize("dtype_name,tol", [("float32", 1e-4), ("float64", 1e-11)])
+def test_partitioned_grid_nccl_world2(grid, dtype_name, tol):
+    """The 2-D grid sharding on 2 GPUs in its two degenerate shapes: (2, 1) = two row groups, one column group — the
+    all-gather epilogue carries the exchange, the scatter stays local; (1, 2) = one row group, two column groups — the
+    other way round.  Forward (and CUDA-graph replay) against the sparse oracle."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    err = _run("nccl", "grid", dtype_name, G=48, backward=False, grid=grid)
     assert err < tol, err
 
 
