@@ -167,9 +167,15 @@ def _worker(rank, world, port, backend, mode, dtype_name, result_q, G=6, backwar
 
 def _run(backend, mode, dtype_name, world=2, G=6, backward=True, F=8, grid=None):
     ctx = mp.get_context("spawn")
-    q = ctx.SimpleQueue()
-    mp.spawn(_worker, args=(world, _free_port(), backend, mode, dtype_name, q, G, backward, F, grid), nprocs=world, join=True)
-    return q.get()
+    for attempt in range(3):                     # the rendezvous port is picked by bind-and-release: retry if someone took it
+        q = ctx.SimpleQueue()
+        try:
+            mp.spawn(_worker, args=(world, _free_port(), backend, mode, dtype_name, q, G, backward, F, grid), nprocs=world,
+                     join=True)
+            return q.get()
+        except Exception as exc:
+            if "EADDRINUSE" not in str(exc) or attempt == 2:
+                raise
 
 
 @pytest.mark.parametrize("mode,G", [("nodes", 6), ("features", 6), ("features", 5)])
