@@ -297,6 +297,7 @@ struct BcastArgs {
   int64_t row0;           // global index of this rank's first row
   int64_t out_ld;
   int n_peers;
+  int split_store;        // peer stores as two 16-byte halves instead of one 32-byte store (B200GF_PEER_STORE128=1, A/B runs)
 };
 
 template <int VEC>
@@ -321,6 +322,15 @@ __device__ __forceinline__ void bcast_store(const BcastArgs<T>& bc, int64_t row,
   const int64_t off = (bc.row0 + row) * bc.out_ld + cbase;
   if (bc.mc != nullptr) {
     multimem_store<VEC>(bc.mc + off, acc);
+  } else if (VEC * sizeof(T) == 32 && bc.split_store) {
+    constexpr int H = VEC / 2;
+    Acc<T, H> lo, hi;
+#pragma unroll
+    for (int i = 0; i < H; ++i) { lo.v[i] = acc.v[i]; hi.v[i] = acc.v[H + i]; }
+    for (int q = 0; q < bc.n_peers; ++q) {
+      store_vec<T, H, 0>(bc.peer[q] + off, lo);
+      store_vec<T, H, 0>(bc.peer[q] + off + H, hi);
+    }
   } else {
     for (int q = 0; q < bc.n_peers; ++q) store_vec<T, VEC, 0>(bc.peer[q] + off, acc);
   }
