@@ -563,6 +563,8 @@ class PartitionedLSIGF:
             opb = (Rc * row_elems * es + 255) // 256 * 256
             ar = SymmetricArena(self.ops.lib, T * buf + 2 * opb, self.group, self.device, prefer=self.symm_backend)
             ar.buf_bytes, ar.op_bytes, ar.op_off = buf, opb, T * buf
+            ar.mc = 0                                      # the grid epilogue uses peer stores only
+            ar.kind = ar.kind.replace("+multicast", " (multicast available, peer stores used)")
             self._arenas[key] = ar
         pbuf = self._grid_step & 1
         self._grid_step += 1
