@@ -43,8 +43,6 @@ static BcastArgs<T> make_bcast(const BcastHost* bh) {
   for (int i = 0; i < bh->n_peers; ++i) bc.peer[i] = reinterpret_cast<T*>(bh->peer[i]);
   bc.mc = reinterpret_cast<T*>(bh->mc);
   bc.row0 = bh->row0; bc.out_ld = bh->out_ld; bc.n_peers = bh->n_peers;
-  static const int split = [] { const char* e = getenv("B200GF_PEER_STORE128"); return (e && e[0] == '1') ? 1 : 0; }();
-  bc.split_store = split;
   return bc;
 }
 

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../graph-neural-networks_b200/csrc/spmm_kernels.cuh"
+#include "spmm_async_variant.cuh"
 
 using namespace b200gf;
 
