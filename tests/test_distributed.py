@@ -238,3 +238,25 @@ def test_unpack_tap_grads_is_the_adjoint_of_pack_taps():
         dh = _unpack_tap_grads(dW, E, K)
         assert dh.shape == hp.shape
         assert abs(float((dh * hp).sum() - (dW * packed).sum())) < 1e-10
+
+
+def test_grid_geometry_host_logic():
+    """2-D grid bookkeeping that needs no GPU: the default factorisation, and that the tiles of all ranks tile x exactly
+    (rows of the row group, zero padding, features of the column group)."""
+    from gnn_b200.distributed import default_grid, PartitionedLSIGF
+    assert default_grid(8) == (2, 4) and default_grid(4) == (2, 2) and default_grid(2) == (2, 1) and default_grid(3) == (3, 1)
+    N, B, G, P = 203, 2, 16, 8
+    Pr, Pc = default_grid(P)
+    Rc = (N + P - 1) // P
+    x = torch.arange(N * B * G, dtype=torch.float64).reshape(N, B * G)
+    covered = torch.zeros(Rc * P, B, G)
+    for rank in range(P):
+        part = PartitionedLSIGF.__new__(PartitionedLSIGF)          # geometry only: no process group, no plan
+        part.Pr, part.Pc, part.rg, part.cg = Pr, Pc, rank // Pc, rank % Pc
+        part.rows_per_rank, part.rows_per_group, part.n_pad = Rc, Rc * Pc, Rc * P
+        tile = part.grid_tile(x, B, G)
+        Gl = G // Pc
+        assert tuple(tile.shape) == (Rc * Pc, B * Gl)
+        r0 = part.rg * Rc * Pc
+        covered[r0:r0 + Rc * Pc, :, part.cg * Gl:(part.cg + 1) * Gl] += tile.view(Rc * Pc, B, Gl)
+    assert torch.equal(covered[:N].reshape(N, B * G), x) and float(covered[N:].abs().max()) == 0.0
