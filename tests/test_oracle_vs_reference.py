@@ -248,3 +248,65 @@ def test_reference_gatedgrnn_with_biases_after_install(monkeypatch):
     # shapes the reference's broadcast would reject are still rejected loudly
     with pytest.raises(RuntimeError, match="bias must broadcast"):
         gnn_b200.LSIGF(a, S, x[:, 0], torch.zeros(H + 1, 1, dtype=torch.float64))
+
+
+def test_fuse_layers_on_a_reference_architecture(monkeypatch):
+    """SURVEY.md §8 f-1 at the architecture level: an unmodified reference `SelectionGNN` with two graph-convolutional
+    layers and `MaxPoolLocal` (architectures.py:166-296), built once with the reference's own layers and once after
+    install() + fuse_layers() with this package's — same seeds, same parameters.  Output, input gradient and every
+    parameter gradient must agree; the state_dict keys must not change.  CPU: the oracle / a torch gather stand in for the
+    two CUDA dispatch hooks, everything else (fused-activation plumbing, Identity rewiring, neighbourhoods) is product code."""
+    import torch.nn as nn
+    import gnn_b200
+    from gnn_b200 import graphML, pooling
+    gml = ref_import.import_reference()
+    import alegnn.modules.architectures as archit
+
+    def dispatch(h, S, x, b, act=0):
+        y = orc.lsigf_dense_torch(h, S, x, b)
+        return torch.relu(y) if act else y
+
+    def gather_max(x, nb32, n_out, max_nb):
+        B, F, _ = x.shape
+        return x.index_select(2, nb32.reshape(-1).long()).reshape(B, F, n_out, max_nb).max(dim=3)[0]
+
+    rng = np.random.default_rng(21)
+    N = 24
+    A = (rng.random((N, N)) < 0.2).astype(np.float64)
+    A = np.maximum(A, A.T)
+    np.fill_diagonal(A, 0)
+    S = A / max(np.abs(np.linalg.eigvalsh(A)).max(), 1e-9)
+    x = torch.tensor(rng.standard_normal((3, 2, N)))
+
+    def build():
+        torch.manual_seed(5)
+        torch.set_default_dtype(torch.float64)
+        try:
+            return archit.SelectionGNN([2, 4, 3], [3, 2], True, nn.ReLU, [10, 6], gml.MaxPoolLocal, [1, 2], [5], S)
+        finally:
+            torch.set_default_dtype(torch.float32)
+
+    ref_net = build()
+    xr = x.clone().requires_grad_(True)
+    y_ref = ref_net(xr)
+    y_ref.sum().backward()
+    try:
+        gnn_b200.install(gml)
+        monkeypatch.setattr(graphML, "_dispatch", dispatch)
+        monkeypatch.setattr(pooling, "_gather_max", gather_max)
+        net = build()
+        assert isinstance(net.GFL[0], gnn_b200.GraphFilter) and isinstance(net.GFL[2], gnn_b200.MaxPoolLocal)
+        assert sorted(net.state_dict().keys()) == sorted(ref_net.state_dict().keys())
+        net.load_state_dict(ref_net.state_dict())
+        assert gnn_b200.fuse_layers(net) == 2
+        assert isinstance(net.GFL[1], nn.Identity) and isinstance(net.GFL[4], nn.Identity)
+        assert sorted(net.state_dict().keys()) == sorted(ref_net.state_dict().keys())
+        xm = x.clone().requires_grad_(True)
+        y = net(xm)
+        y.sum().backward()
+    finally:
+        gnn_b200.uninstall(gml)
+    assert _rel(y.detach().numpy(), y_ref.detach().numpy()) < 1e-12
+    assert _rel(xm.grad.numpy(), xr.grad.numpy()) < 1e-11
+    for (n1, p1), (n2, p2) in zip(sorted(ref_net.named_parameters()), sorted(net.named_parameters())):
+        assert n1 == n2 and _rel(p2.grad.numpy(), p1.grad.numpy()) < 1e-11, n1
