@@ -183,6 +183,12 @@ class SymmetricArena:
                     raise
                 self._why_not_torch = repr(exc)[:200]
                 self.peers = None
+            # the choice must be the same on every rank (the IPC path below is collective): all or nothing
+            ok = torch.tensor([0 if self.peers is None else 1], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0 and self.peers is not None:
+                self.peers, self.mc, self._keep, self.kind = None, 0, None, None
+                self._why_not_torch = "torch symmetric memory failed on another rank"
         if self.peers is None:
             mine = ctypes.c_void_p()
             _cabi.check(lib.b200gf_symm_alloc(ctypes.byref(mine), total))      # zero-filled
