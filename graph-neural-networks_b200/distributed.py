@@ -56,6 +56,15 @@ def transpose_csr(csr, N):
     return m.indptr.astype(np.int64), m.indices.astype(np.int32), m.data
 
 
+def resolve_fused(requested, ops_injected, backend, world):
+    """Whether the hop kernels move their rows over NVLink themselves (no NCCL collective on the data path).
+    `requested` None = default: on whenever the real CUDA ops run under NCCL with at most 16 ranks (the peer-pointer
+    arrays of the kernels hold 16 entries); True / False = the caller's explicit choice."""
+    if requested is None:
+        return bool((not ops_injected) and backend == "nccl" and world <= 16)
+    return bool(requested)
+
+
 def default_grid(world):
     """(P_r, P_c) for the 2-D sharding: two row groups, the rest column groups (8 -> 2 x 4, 4 -> 2 x 2)."""
     if world >= 4 and world % 2 == 0:
@@ -367,12 +376,9 @@ class PartitionedLSIGF:
             self.local_nnz = gso.nnz()
             self.plan = self.ops.make_plan_full(gso)
         self._bufs = {}
-        if self._fused_req is None:
-            self.fused = (ops is None and dist.get_backend(group) == "nccl" and self.world <= 16)
+        self.fused = resolve_fused(self._fused_req, ops is not None, dist.get_backend(group), self.world)
         if mode == "grid" and not self.fused:
             raise RuntimeError("b200gf: the grid sharding exists only as the fused CUDA path (NCCL process group, <= 16 ranks)")
-        else:
-            self.fused = bool(self._fused_req)
 
     def close(self):
         """Collective: release the symmetric memory of this object (arenas of the node sharding, operands of the feature

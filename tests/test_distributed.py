@@ -114,10 +114,14 @@ def _worker(rank, world, port, backend, mode, dtype_name, result_q, G=6, backwar
         else:
             g0, g1 = part.feature_slice(G)
             x_local = xn.view(N, B, G)[:, :, g0:g1].reshape(N, B * (g1 - g0)).contiguous().to(dev)
+        if backend == "nccl":
+            # default construction under NCCL = the kernels move their rows over NVLink themselves; a silent fall back to
+            # the NCCL-collective path would leave the fused kernels untested
+            assert part.fused, "default PartitionedLSIGF under NCCL must take the fused path"
         for _ in range(2):  # twice: buffers are reused across calls
             y_local = part.forward(ht, x_local, bt, B=B)
         assert tuple(y_local.shape) == (R, B * F)
-        if backend == "nccl" and getattr(part, "fused", False) and G % (4 * world) == 0:
+        if backend == "nccl" and G % (4 * world) == 0:
             # the same step replayed as CUDA graphs (peer-flag fence, no NCCL inside): must reproduce the eager result
             run = part.graphed(ht, x_local, bt, B=B)
             for _ in range(3):
@@ -238,6 +242,18 @@ def test_unpack_tap_grads_is_the_adjoint_of_pack_taps():
         dh = _unpack_tap_grads(dW, E, K)
         assert dh.shape == hp.shape
         assert abs(float((dh * hp).sum() - (dW * packed).sum())) < 1e-10
+
+
+def test_fused_default_resolution():
+    """`fused=None` means: fused whenever the real CUDA ops run under NCCL with <= 16 ranks; explicit choices are kept."""
+    from gnn_b200.distributed import resolve_fused
+    assert resolve_fused(None, False, "nccl", 2) is True
+    assert resolve_fused(None, False, "nccl", 16) is True
+    assert resolve_fused(None, False, "nccl", 32) is False          # peer arrays of the kernels hold 16 pointers
+    assert resolve_fused(None, False, "gloo", 2) is False
+    assert resolve_fused(None, True, "nccl", 2) is False            # injected (CPU stand-in) ops
+    assert resolve_fused(True, True, "gloo", 2) is True and resolve_fused(False, False, "nccl", 2) is False
+    assert resolve_fused(0, False, "nccl", 2) is False
 
 
 def test_grid_geometry_host_logic():
