@@ -476,7 +476,14 @@ class PartitionedLSIGF:
         ([rows_per_rank, C]) with the forward (z S_e) or backward (S_e z) operator.  Every hop that has a successor runs
         b200gf_hop_bcast: its rows land in the full-height matrix of every rank (NVLink peer stores or one NVSwitch
         multicast store per row) while the kernel is still gathering, a peer-flag fence separates the hops; the last hop
-        of a chain stays local.  No NCCL call, no host synchronisation."""
+        of a chain stays local.  No NCCL call, no host synchronisation.
+
+        Hazards across calls (same arena reused by the next step): a rank may store into a peer's buffer t only after it
+        passed a fence that the peer signals after its last read of buffer t.  Buffer t >= 1 is written by hop t of the
+        next call, which follows that call's z_0 fence; the peer signals that fence after everything it enqueued for
+        this call.  Buffer 0 is written first thing in the next call, so its readers (hop 1 of every chain) must precede
+        the last fence of this call: true for K >= 3 (fence after hop K-2 of the last chain), enforced for K == 2 by
+        the trailing fence below."""
         C = rows.shape[1]
         ld = _pad_ld(C, self.dtype)
         es = rows.element_size()
@@ -502,6 +509,11 @@ class PartitionedLSIGF:
                     self.ops.hop(self.plan, e, direction, src, local_rows(t), C)
                 out.append(local_rows(t))
                 src = local_full(t)
+        if K == 2:
+            # with a single hop per chain nothing above orders "every rank has read z_0" before a faster rank's next call
+            # stores its new z_0 rows into this rank's buffer 0; for K >= 3 the fence after hop K-2 of the last chain does
+            # (every reader of buffer 0 precedes it in stream order)
+            ar.fence(st)
         return out
 
     def _forward_nodes_fused(self, h, x_rows, b):
