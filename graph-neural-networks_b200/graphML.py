@@ -335,7 +335,8 @@ def install(gml=None):
                                                              "MaxPoolLocal", "MaxLocalActivation",
                                                              "MedianLocalActivation", "HiddenState",
                                                              "TimeGatedHiddenState", "NodeGatedHiddenState",
-                                                             "LSIGF_DB", "GraphFilter_DB")})
+                                                             "LSIGF_DB", "GraphFilter_DB", "GRNN_DB",
+                                                             "HiddenState_DB")})
     gml.LSIGF = LSIGF
     gml.GraphFilter = GraphFilter
     gml.EVGF = edgevariant.EVGF
@@ -348,10 +349,12 @@ def install(gml=None):
     gml.HiddenState = recurrent.HiddenState
     gml.TimeGatedHiddenState = recurrent.TimeGatedHiddenState
     gml.NodeGatedHiddenState = recurrent.NodeGatedHiddenState
-    # batch-/time-varying GSOs: one space-time sparse operator per batch (delayed.py).  GRNN_DB looks LSIGF_DB up as a
-    # module global (graphML.py:1164), so its input-to-hidden filter is retargeted as well.
+    # batch-/time-varying GSOs: one space-time sparse operator per batch (delayed.py)
     gml.LSIGF_DB = delayed.LSIGF_DB
     gml.GraphFilter_DB = delayed.GraphFilter_DB
+    # the recursion over the same GSO batch: the delay line advanced by one CSR hop per time step (delayed.GRNN_DB)
+    gml.GRNN_DB = delayed.GRNN_DB
+    gml.HiddenState_DB = delayed.HiddenState_DB
     return gml
 
 

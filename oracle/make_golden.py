@@ -298,11 +298,74 @@ def gen_lsigf_db(gml):
     print("lsigf_db_cases.npz:", sorted(k for k in out if k.endswith("_y")))
 
 
+def gen_grnn_db(gml):
+    """GRNN_DB (graphML.py:1096-1290) and HiddenState_DB (graphML.py:3395-3538): hidden-state recursion on a GSO that
+    changes with the batch element and the time step; fp64 forward and autograd gradients of every input.
+    The reference builds its K x (K-1) selection matrix with the default dtype (:1176), so it runs in fp64 only with the
+    default dtype set accordingly."""
+    out = {}
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        # (tag, B, T, N, F, H, K, E, bias, sigma)
+        cases = [("a", 3, 5, 7, 2, 3, 3, 1, True, "tanh"), ("b", 2, 6, 6, 3, 2, 4, 2, True, "tanh"),
+                 ("c", 2, 1, 5, 2, 2, 3, 1, True, "tanh"),       # a single time step: no shift at all
+                 ("d", 1, 6, 8, 1, 4, 1, 1, False, "relu"),      # K = 1: no delay line
+                 ("e", 2, 3, 9, 4, 5, 6, 1, True, "tanh"),       # more taps than time steps
+                 ("f", 2, 7, 6, 2, 3, 2, 2, False, "relu")]      # K = 2, E = 2
+        for (tag, B, T, N, F, H, K, E, bias, sg) in cases:
+            rng = np.random.default_rng(700 + ord(tag))
+            S = np.stack([np.stack([orc.random_sparse_gso(rng, N, 3, E) for _ in range(T)]) for _ in range(B)])
+            x = rng.standard_normal((B, T, F, N))
+            z0 = rng.standard_normal((B, H, N))
+            a = rng.uniform(-0.5, 0.5, (H, E, K, F))
+            b = rng.uniform(-0.5, 0.5, (H, E, K, H))
+            xb = rng.uniform(-0.5, 0.5, (H, 1)) if bias else None
+            zb = rng.uniform(-0.5, 0.5, (H, 1)) if bias else None
+            ts = [torch.tensor(v, requires_grad=True) for v in (a, b, x, z0)]
+            bs = [None if v is None else torch.tensor(v, requires_grad=True) for v in (xb, zb)]
+            z = gml.GRNN_DB(ts[0], ts[1], torch.tensor(S), ts[2], ts[3], getattr(torch, sg), bs[0], bs[1])
+            dz = rng.standard_normal(tuple(z.shape))
+            z.backward(torch.tensor(dz))
+            key = "g" + tag
+            out[key + "_meta"] = np.array([B, T, N, F, H, K, E, int(bias), {"tanh": 0, "relu": 1}[sg]])
+            for name, val in (("S", S), ("x", x), ("z0", z0), ("a", a), ("b", b), ("dz", dz), ("z", z.detach().numpy()),
+                              ("da", ts[0].grad.numpy()), ("db", ts[1].grad.numpy()), ("dx", ts[2].grad.numpy()),
+                              ("dz0", ts[3].grad.numpy())):
+                out[key + "_" + name] = val
+            if bias:
+                out[key + "_xb"], out[key + "_zb"] = xb, zb
+                out[key + "_dxb"], out[key + "_dzb"] = bs[0].grad.numpy(), bs[1].grad.numpy()
+        # the layer
+        B, T, N, F, H, K, E = 3, 5, 6, 2, 4, 3, 2
+        rng = np.random.default_rng(760)
+        S = np.stack([np.stack([orc.random_sparse_gso(rng, N, 3, E) for _ in range(T)]) for _ in range(B)])
+        torch.manual_seed(760)
+        layer = gml.HiddenState_DB(F, H, K, torch.tanh, E, True).double()
+        layer.addGSO(torch.tensor(S))
+        x, z0 = rng.standard_normal((B, T, F, N)), rng.standard_normal((B, H, N))
+        xt, zt = torch.tensor(x, requires_grad=True), torch.tensor(z0, requires_grad=True)
+        z, zT = layer(xt, zt)
+        dz, dzT = rng.standard_normal(tuple(z.shape)), rng.standard_normal(tuple(zT.shape))
+        ((z * torch.tensor(dz)).sum() + (zT * torch.tensor(dzT)).sum()).backward()
+        out.update({"layer_meta": np.array([B, T, N, F, H, K, E]), "layer_S": S, "layer_x": x, "layer_z0": z0,
+                    "layer_dz": dz, "layer_dzT": dzT, "layer_z": z.detach().numpy(), "layer_zT": zT.detach().numpy(),
+                    "layer_dx": xt.grad.numpy(), "layer_dz0": zt.grad.numpy()})
+        for name, prm in layer.named_parameters():
+            out["layer_p_" + name] = prm.detach().numpy()
+            out["layer_g_" + name] = prm.grad.numpy()
+    finally:
+        torch.set_default_dtype(prev)
+    np.savez_compressed(os.path.join(OUT, "grnn_db_cases.npz"), **out)
+    print("grnn_db_cases.npz:", sorted(k for k in out if k.endswith("_z")))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gml = ref_import.import_reference()
     only = set(sys.argv[1:])                               # e.g. `python oracle/make_golden.py grnn`
     for name, gen in (("lsigf", gen_lsigf), ("graphfilter", gen_graphfilter), ("selectiongnn_cfg1", gen_selectiongnn_cfg1),
-                      ("evgf", gen_evgf), ("grnn", gen_grnn), ("lsigf_db", gen_lsigf_db), ("layer", gen_layer)):
+                      ("evgf", gen_evgf), ("grnn", gen_grnn), ("lsigf_db", gen_lsigf_db), ("layer", gen_layer),
+                      ("grnn_db", gen_grnn_db)):
         if not only or name in only:
             gen(gml)
