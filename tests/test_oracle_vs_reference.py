@@ -177,6 +177,62 @@ def test_install_retargets_batch_delay_filter(monkeypatch):
     assert (gml.LSIGF_DB, gml.GraphFilter_DB) == orig
 
 
+def test_install_retargets_batch_delay_recurrence(monkeypatch):
+    """GraphRecurrentNN_DB (architecturesTime.py:273-470: HiddenState_DB -> GraphFilter_DB -> tanh -> per-node readout) built
+    from the retargeted module equals the unmodified architecture, output and every parameter gradient; torch.sparse on the
+    per-time-step CSR operators stands in for the hop kernel, the dense CPU oracle for the filters."""
+    import gnn_b200
+    from gnn_b200 import delayed
+    gml = ref_import.import_reference()
+    import alegnn.modules.architecturesTime as architTime
+    orig = (gml.GRNN_DB, gml.HiddenState_DB)
+    rng = np.random.default_rng(4)
+    B, T, N, E = 2, 6, 7, 2
+    S = torch.tensor(np.stack([np.stack([orc.random_sparse_gso(rng, N, 3, E) for _ in range(T)]) for _ in range(B)]),
+                     dtype=torch.float32)
+    x = torch.tensor(rng.standard_normal((B, T, 2, N)), dtype=torch.float32)
+
+    def build_and_run():
+        torch.manual_seed(22)                       # parameters, then the random initial hidden state (:447)
+        net = architTime.GraphRecurrentNN_DB(2, 3, 4, [3, 2], True, torch.tanh, torch.tanh, torch.nn.Tanh, [5, 2], E)
+        y = net(x, S)
+        y.sum().backward()
+        return net, y, [p.grad.clone() for p in net.parameters()]
+
+    _, y_ref, g_ref = build_and_run()
+
+    def apply(h, S_, x_big, b_big):
+        csr, M = delayed.block_delay_csr(S_)
+        dense = torch.zeros(len(csr), M, M, dtype=S_.dtype)
+        for e, (rowptr, col, val) in enumerate(csr):
+            dense[e, torch.repeat_interleave(torch.arange(M), rowptr[1:] - rowptr[:-1]), col.long()] = val
+        return orc.lsigf_dense_torch(h, dense, x_big, b_big)
+
+    class SparseSlabOps:
+        def __init__(self, S_):
+            fwd, _, R = delayed.slab_csr(S_)
+            self.A = [torch.sparse_coo_tensor(torch.stack((torch.repeat_interleave(torch.arange(R), rp[1:] - rp[:-1]), col.long())),
+                                              val, (R, R)) for (rp, col, val) in fwd]
+
+        def hop(self, o, src):
+            return torch.sparse.mm(self.A[o], src)
+
+    try:
+        gnn_b200.install(gml)
+        monkeypatch.setattr(delayed, "_apply", apply)
+        monkeypatch.setattr(delayed, "_slab_ops", SparseSlabOps)
+        net, y, g = build_and_run()
+        assert isinstance(net.hiddenState, gnn_b200.HiddenState_DB) and isinstance(net.outputState, gnn_b200.GraphFilter_DB)
+        assert {"hiddenState.aWeights", "hiddenState.bWeights", "hiddenState.xBias", "hiddenState.zBias",
+                "outputState.weight", "outputState.bias"} <= set(net.state_dict())
+        assert y.shape == y_ref.shape and torch.allclose(y, y_ref, rtol=1e-5, atol=1e-6)
+        for a, b in zip(g, g_ref):
+            assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
+    finally:
+        gnn_b200.uninstall(gml)
+    assert (gml.GRNN_DB, gml.HiddenState_DB) == orig
+
+
 @pytest.mark.parametrize("dataType", [np.float64, torch.float64])
 def test_sparse_source_localization_matches_reference_dataset(dataType):
     """gnn_b200.datasets_sparse.SourceLocalization (sparse mat-vec diffusion) == the reference data class
