@@ -856,7 +856,10 @@ class PartitionedLSIGF:
         """CUDA-graph version of the fused features path for a fixed input buffer: two graphs (one per operand buffer)
         are captured after two eager warm-up calls and replayed alternately, so a step costs one graph launch on the
         host.  Needs fence="flags" (everything in the step is then a kernel of this library or a device copy).
-        Returns a callable; each call replays one step on the current contents of x_static / h / b."""
+        Returns a callable; each call replays one step on the current contents of x_static / h / b.
+        The two graphs own the two buffer parities: do not interleave eager forward() calls on this object with replays
+        unless a collective on the stream (e.g. dist.barrier()) separates them on every rank — two consecutive steps on
+        the same operand buffer have no fence between a fast rank's stores and a slow rank's contraction."""
         assert self.fused and self.fence == "flags"
         for _ in range(2):
             self.forward(h, x_static, b, B)
