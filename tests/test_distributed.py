@@ -80,7 +80,7 @@ def _case(N=203, B=2, G=6, F=8, K=4, E=2, seed=3):
     return mats, x, h, b
 
 
-def _worker(rank, world, port, backend, mode, dtype_name, result_q, G=6, backward=True, F=8, grid=None):
+def _worker(rank, world, port, backend, mode, dtype_name, result_q, G=6, backward=True, F=8, grid=None, K=4):
     import gnn_b200
     from gnn_b200.distributed import PartitionedLSIGF
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -96,7 +96,7 @@ def _worker(rank, world, port, backend, mode, dtype_name, result_q, G=6, backwar
         dist.init_process_group("gloo", rank=rank, world_size=world)
         ops = OracleOps()
     try:
-        mats, x, h, b = _case(G=G, F=F)
+        mats, x, h, b = _case(G=G, F=F, K=K)
         B, G, N = x.shape
         F = h.shape[0]
         gso = gnn_b200.SparseGSO.from_scipy(mats, dtype=dtype)
@@ -169,12 +169,12 @@ def _worker(rank, world, port, backend, mode, dtype_name, result_q, G=6, backwar
         dist.destroy_process_group()
 
 
-def _run(backend, mode, dtype_name, world=2, G=6, backward=True, F=8, grid=None):
+def _run(backend, mode, dtype_name, world=2, G=6, backward=True, F=8, grid=None, K=4):
     ctx = mp.get_context("spawn")
     for attempt in range(3):                     # the rendezvous port is picked by bind-and-release: retry if someone took it
         q = ctx.SimpleQueue()
         try:
-            mp.spawn(_worker, args=(world, _free_port(), backend, mode, dtype_name, q, G, backward, F, grid), nprocs=world,
+            mp.spawn(_worker, args=(world, _free_port(), backend, mode, dtype_name, q, G, backward, F, grid, K), nprocs=world,
                      join=True)
             return q.get()
         except Exception as exc:
@@ -187,6 +187,13 @@ def test_partitioned_gloo_world2(mode, G):
     """G = 6: all-to-all exchange of the shifted slices; G = 5 (not divisible by 2): reduce-scatter variant.
     Forward and backward (dh, dx, db) against the sparse oracle."""
     err = _run("gloo", mode, "float64", G=G)
+    assert err < 1e-12, err
+
+
+@pytest.mark.parametrize("mode,K", [("nodes", 2), ("nodes", 1), ("features", 2)])
+def test_partitioned_gloo_world2_short_filters(mode, K):
+    """K = 2: a single hop per chain (the last hop of a chain is never exchanged); K = 1: no hop at all."""
+    err = _run("gloo", mode, "float64", K=K)
     assert err < 1e-12, err
 
 
