@@ -1,6 +1,7 @@
 """Multi-GPU LSIGF (one process per GPU, torch.distributed over NCCL / NVLink 5) — SURVEY.md §8e.
 
-Two shardings of  y = sum_{e,k} (x S_e^k) h_{e,k} + b :
+Three shardings of  y = sum_{e,k} (x S_e^k) h_{e,k} + b  (each with its exchange fused into the hop kernel when the real
+CUDA ops run under NCCL, and with plain collectives otherwise — the variant the gloo tests exercise):
 
   mode="nodes"     1-D node partition.  Rank p owns rows [r_p, r_{p+1}) of every node-major matrix and the matching
                    rows of the gather operators (global column indices).  Each of the K-1 hops is followed by an
@@ -14,14 +15,15 @@ Two shardings of  y = sum_{e,k} (x S_e^k) h_{e,k} + b :
                    call (output sharded by node rows).  The right choice whenever S fits on each GPU (SURVEY §8e
                    "column split"); a reduce-scatter variant covers G not divisible by the world size.
 
-  mode="grid"      2-D process grid P = P_r x P_c (CUDA only): rank (r, c) shifts the rows of row group r for the columns of
+  mode="grid"      2-D process grid P = P_r x P_c: rank (r, c) shifts the rows of row group r for the columns of
                    column group c.  Each hop all-gathers its rows inside the column group (P_r ranks, N*C/P_c elements
                    instead of N*C) and delivers its slice to the contraction owner inside the row group — both from the
                    kernel's epilogue (b200gf_hop_grid).  The all-gather that bounds the node sharding at 8 GPUs and the
-                   replicated index work that bounds the feature sharding are both cut by the grid factors.
+                   replicated index work that bounds the feature sharding are both cut by the grid factors.  The
+                   backward exists in the collective form only.
 
 The arithmetic goes through `ops` (the C-ABI building blocks b200gf_hop / b200gf_tap_contract on CUDA).  The
-world_size-2 gloo tests inject an oracle-backed `ops` to exercise the partitioning / collective choreography on CPU;
+world_size-2 / -4 gloo tests inject an oracle-backed `ops` to exercise the partitioning / collective choreography on CPU;
 the product default has no CPU path.
 """
 import numpy as np
@@ -364,6 +366,7 @@ class PartitionedLSIGF:
             self.local_nnz = int(sum(f[0][-1] for f in fwd))
             self.plan = self.ops.make_plan_ops(fwd, None, self.rows_per_group, self.n_pad, self.dtype)
             self._grid_step = 0
+            self._grid_gso = gso                                                  # backward: rows of S_e, plan built on first use
         elif mode == "nodes":
             fwd, bwd = [], []
             for e in range(self.E):
@@ -377,8 +380,8 @@ class PartitionedLSIGF:
             self.plan = self.ops.make_plan_full(gso)
         self._bufs = {}
         self.fused = resolve_fused(self._fused_req, ops is not None, dist.get_backend(group), self.world)
-        if mode == "grid" and not self.fused:
-            raise RuntimeError("b200gf: the grid sharding exists only as the fused CUDA path (NCCL process group, <= 16 ranks)")
+        self._grid_groups_cache = None
+        self._grid_bwd_plan = None
 
     def close(self):
         """Collective: release the symmetric memory of this object (arenas of the node sharding, operands of the feature
@@ -410,7 +413,9 @@ class PartitionedLSIGF:
     def forward(self, h, x_local, b=None, B=1):
         """B (batch size) is only read in features mode, where it cannot be inferred from an empty column slice."""
         if self.mode == "grid":
-            return self._forward_grid(h, x_local, b, B)
+            if self.fused and self._grid_fused_ok(h.shape[3], B):
+                return self._forward_grid(h, x_local, b, B)
+            return self._forward_grid_collective(h, x_local, b, B)
         if self.mode == "nodes":
             if self.fused and self._nodes_fused_ok(x_local.shape[1]):
                 return self._forward_nodes_fused(h, x_local, b)
@@ -571,9 +576,9 @@ class PartitionedLSIGF:
         Gl = G // Pc
         Cl = B * Gl
         q = 8 if self.dtype == torch.float32 else 4
-        if Gl % q != 0 or Cl < 2 * q:
-            raise RuntimeError("b200gf: grid sharding needs G / P_c a multiple of %d columns (32-byte lanes) and rows of at "
-                               "least 64 bytes; got G = %d, P_c = %d, B = %d" % (q, G, Pc, B))
+        if Gl % q != 0 or Cl < 2 * q:                                  # forward() routes such shapes to the collective variant
+            raise RuntimeError("b200gf: the fused grid kernels need G / P_c a multiple of %d columns (32-byte lanes) and rows "
+                               "of at least 64 bytes; got G = %d, P_c = %d, B = %d" % (q, G, Pc, B))
         Rc, Rr = self.rows_per_rank, self.rows_per_group
         assert x_tile.shape[0] == Rr and x_tile.shape[1] == Cl
         T = 1 + E * (K - 1)
@@ -625,6 +630,142 @@ class PartitionedLSIGF:
             bias = b.contiguous()
         self.ops.tap_contract([ar.local(ar.op_off + pbuf * ar.op_bytes, row_elems)], W, bias, y, Rc, B, T * G, F)
         return y[:, :B * F]
+
+    # -- 2-D process grid, collective variant (and the backward) --------------------------------------------
+    def _grid_fused_ok(self, G, B):
+        q = 8 if self.dtype == torch.float32 else 4
+        return G % self.Pc == 0 and (G // self.Pc) % q == 0 and B * (G // self.Pc) >= 2 * q
+
+    def _grid_groups(self):
+        """(row group, column group) process groups of this rank; None for a group of one.  Collective on first use: every
+        rank of `self.group` creates every sub-group, in the same order (torch.distributed's rule for new_group)."""
+        if self._grid_groups_cache is None:
+            base = dist.get_process_group_ranks(self.group) if self.group is not None else list(range(self.world))
+            Pr, Pc = self.Pr, self.Pc
+            rows = [dist.new_group([base[r * Pc + c] for c in range(Pc)]) if Pc > 1 else None for r in range(Pr)]
+            cols = [dist.new_group([base[r * Pc + c] for r in range(Pr)]) if Pr > 1 else None for c in range(Pc)]
+            self._grid_groups_cache = (rows[self.rg], cols[self.cg])
+        return self._grid_groups_cache
+
+    def _grid_gather_rows(self, full, colg):
+        """all-gather of the row-group blocks of a full-height matrix inside the column group (in place)."""
+        if colg is not None:
+            g0 = self.rg * self.rows_per_group
+            dist.all_gather_into_tensor(full.view(-1), full[g0:g0 + self.rows_per_group].reshape(-1), group=colg)
+
+    def _grid_operand(self, E, K, G, x_tile, B):
+        """The row-local contraction operand [rows_per_rank, B*T*G] (column b*T*G + t*G + g) of this rank: K-1 hops per
+        edge feature on the rank's tile (rows of its row group x features of its column group), every hop output
+        all-gathered inside the column group, then one all-to-all inside the row group hands every rank the slices of its
+        own rows.  Same data flow as the fused kernel's two epilogues (_forward_grid), with collectives."""
+        Pr, Pc = self.Pr, self.Pc
+        assert G % Pc == 0, "the grid sharding splits the G input features evenly over the column groups"
+        Gl = G // Pc
+        Cl = B * Gl
+        Rc, Rr = self.rows_per_rank, self.rows_per_group
+        assert x_tile.shape[0] == Rr and x_tile.shape[1] == Cl
+        T = 1 + E * (K - 1)
+        rowg, colg = self._grid_groups()
+        ld = _pad_ld(Cl, self.dtype)
+        g0 = self.rg * Rr
+        full0 = self._buffers(("gz0", Cl), (self.n_pad, ld))
+        full0[g0:g0 + Rr, :Cl].copy_(x_tile)
+        if K > 1:
+            self._grid_gather_rows(full0, colg)
+        tiles = [full0[g0:g0 + Rr]]
+        for e in range(E):
+            src = full0
+            for k in range(1, K):
+                if k == K - 1:
+                    dst = self._buffers(("gzl", e, Cl), (Rr, ld))
+                    self.ops.hop(self.plan, e, _cabi.HOP_FWD, src, dst, Cl)
+                else:
+                    full = self._buffers(("gz", e, k, Cl), (self.n_pad, ld))
+                    dst = full[g0:g0 + Rr]
+                    self.ops.hop(self.plan, e, _cabi.HOP_FWD, src, dst, Cl)
+                    self._grid_gather_rows(full, colg)
+                    src = full
+                tiles.append(dst)
+        # block c of `send` = rows of rank (rg, c) inside my row group, my feature slab, every term t
+        send = torch.stack([t_[:, :Cl].reshape(Pc, Rc, Cl) for t_ in tiles], dim=1).contiguous()        # [Pc, T, Rc, Cl]
+        if rowg is not None:
+            recv = torch.empty_like(send)
+            all_to_all_blocks(recv, send, rowg)                 # recv[c] = my rows as computed by rank (rg, c): slab c
+        else:
+            recv = send
+        return recv.reshape(Pc, T, Rc, B, Gl).permute(2, 3, 1, 0, 4).reshape(Rc, B * T * G)
+
+    def _forward_grid_collective(self, h, x_tile, b, B):
+        F, E, K, G = h.shape
+        assert E == self.E
+        T = 1 + E * (K - 1)
+        Rc = self.rows_per_rank
+        zrow = self._grid_operand(E, K, G, x_tile, B)
+        W = self.ops.pack_taps(h, False).reshape(1, T * G, F)
+        y = torch.empty((Rc, _pad_ld(B * F, self.dtype)), dtype=self.dtype, device=self.device)
+        bias = None
+        if b is not None:
+            assert b.shape[1] == 1, "per-node bias is not supported by the partitioned path"
+            bias = b.contiguous()
+        self.ops.tap_contract([zrow], W, bias, y, Rc, B, T * G, F)
+        return y[:, :B * F]
+
+    def _backward_grid_collective(self, h, x_tile, dy_rows, B, want_db):
+        """Gradients for the grid sharding (collectives; the fused forward has no fused backward yet).  dy_rows
+        [rows_per_rank, B*F] of this rank's output rows -> (dh, dx_tile laid out like x_tile, db).
+        dh: the operand Z of the forward is row-local again (recomputed by the same exchange), dW_t = dY^T Z_t over my rows,
+        all-reduced.  dx: U = dY [H_0^T .. H_{T-1}^T] is row-local; one all-to-all inside the row group turns it into
+        tiles (rows of my row group x my feature slab), then Horner with the rows of S_e, every intermediate all-gathered
+        inside the column group."""
+        F, E, K, G = h.shape
+        assert E == self.E
+        Pr, Pc = self.Pr, self.Pc
+        Gl = G // Pc
+        Cl = B * Gl
+        CF = B * F
+        Rc, Rr = self.rows_per_rank, self.rows_per_group
+        T = 1 + E * (K - 1)
+        assert dy_rows.shape[1] == CF
+        rowg, colg = self._grid_groups()
+        dy_rows = dy_rows.contiguous()
+        # ---- dh
+        zrow = self._grid_operand(E, K, G, x_tile, B).view(Rc, B, T, G)
+        zs = [zrow[:, :, t, :].reshape(Rc, B * G) for t in range(T)]
+        dW = self.ops.tap_grad(dy_rows, zs, Rc, B, F, G)                           # [T, F, G] = dY^T Z_t over my rows
+        dist.all_reduce(dW, group=self.group)
+        dh = _unpack_tap_grads(dW, E, K)
+        # ---- dx
+        Wall = self.ops.pack_taps(h, True).permute(1, 0, 2).reshape(1, F, T * G).contiguous()
+        U = torch.empty((Rc, _pad_ld(B * T * G, self.dtype)), dtype=self.dtype, device=self.device)
+        self.ops.tap_contract([dy_rows], Wall, None, U, Rc, B, F, T * G)
+        send = U[:, :B * T * G].reshape(Rc, B, T, Pc, Gl).permute(3, 2, 0, 1, 4).contiguous()        # [Pc, T, Rc, B, Gl]
+        if rowg is not None:
+            recv = torch.empty_like(send)
+            all_to_all_blocks(recv, send, rowg)                 # recv[c] = rows of rank (rg, c), my feature slab
+        else:
+            recv = send
+        Ut = recv.permute(1, 0, 2, 3, 4).reshape(T, Rr, Cl)                        # tiles: rows of my row group
+        dx = Ut[0].clone()                                                          # k = 0 term (shared by every e)
+        if K > 1:
+            if self._grid_bwd_plan is None:
+                g0, g1 = self.rg * Rr, (self.rg + 1) * Rr
+                rows = [row_slice(self._grid_gso.csr[e], g0, g1) for e in range(E)]
+                self._grid_bwd_plan = self.ops.make_plan_ops(rows, None, Rr, self.n_pad, self.dtype)    # S_e w: gather with rows of S_e
+            ld = _pad_ld(Cl, self.dtype)
+            g0 = self.rg * Rr
+            for e in range(E):
+                w = Ut[1 + e * (K - 1) + (K - 2)]                                   # W_{e,K-1} = U_{e,K-1}
+                for k in range(K - 2, -1, -1):                                      # W_{e,k} = U_{e,k} + S_e W_{e,k+1}
+                    full = self._buffers(("gw", k & 1, Cl), (self.n_pad, ld))
+                    full[g0:g0 + Rr, :Cl].copy_(w)
+                    self._grid_gather_rows(full, colg)
+                    out = self._buffers(("go", k & 1, Cl), (Rr, ld))
+                    self.ops.hop(self._grid_bwd_plan, e, _cabi.HOP_FWD, full, out, Cl)
+                    if k > 0:
+                        w = out[:, :Cl] + Ut[1 + e * (K - 1) + (k - 1)]
+                    else:
+                        dx += out[:, :Cl]
+        return dh, dx, (self._bias_grad(dy_rows, B, F) if want_db else None)
 
     def _forward_features(self, h, x_cols, b, B):
         """Column-sharded hops (no communication inside a hop) + an all-to-all of every shifted slice to the rank that
@@ -729,8 +870,7 @@ class PartitionedLSIGF:
         other operator (rows of S_e), exchanged like the forward's; dh and db end in one small all-reduce."""
         assert dy_rows.shape[0] == self.rows_per_rank
         if self.mode == "grid":
-            raise NotImplementedError("b200gf: the 2-D grid sharding has a forward only; train with mode='nodes' (fused "
-                                      "backward) or mode='features'")
+            return self._backward_grid_collective(h, x_local, dy_rows, B, want_db)
         if self.mode == "nodes":
             if self.fused and self._nodes_fused_ok(x_local.shape[1]) and self._nodes_fused_ok(dy_rows.shape[1]):
                 return self._backward_nodes_fused(h, x_local, dy_rows, want_db)

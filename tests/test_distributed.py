@@ -136,7 +136,16 @@ def _worker(rank, world, port, backend, mode, dtype_name, result_q, G=6, backwar
             dyp[:N] = torch.tensor(dy, dtype=dtype).reshape(B * F, N).t()
             hg, xg, bg = (t.clone().requires_grad_(True) for t in (ht, x_local, bt))
             part.apply(hg, xg, bg, B).backward(dyp[part.r0:part.r1].to(dev))
-            if mode == "nodes":
+            if mode == "grid":
+                tiles = [torch.empty_like(xg.grad) for _ in range(world)]      # [rows_per_group, B*(G/P_c)] of rank (rg, cg)
+                dist.all_gather(tiles, xg.grad.contiguous())
+                Rr, Gl = part.rows_per_group, G // part.Pc
+                dx_full = torch.zeros(part.n_pad, B, G, dtype=dtype, device=dev)
+                for p_, t_ in enumerate(tiles):
+                    r_, c_ = p_ // part.Pc, p_ % part.Pc
+                    dx_full[r_ * Rr:(r_ + 1) * Rr, :, c_ * Gl:(c_ + 1) * Gl] = t_.reshape(Rr, B, Gl)
+                dx_nm = dx_full[:N]
+            elif mode == "nodes":
                 dxs = [torch.empty_like(xg.grad) for _ in range(world)]
                 dist.all_gather(dxs, xg.grad.contiguous())
                 dx_nm = torch.cat(dxs)[:N].reshape(N, B, G)
@@ -194,6 +203,15 @@ def test_partitioned_gloo_world2(mode, G):
 def test_partitioned_gloo_world2_short_filters(mode, K):
     """K = 2: a single hop per chain (the last hop of a chain is never exchanged); K = 1: no hop at all."""
     err = _run("gloo", mode, "float64", K=K)
+    assert err < 1e-12, err
+
+
+@pytest.mark.parametrize("world,grid,K", [(4, (2, 2), 4), (2, (2, 1), 4), (2, (1, 2), 4), (4, (2, 2), 2), (4, (4, 1), 3), (4, (1, 4), 1)])
+def test_partitioned_grid_gloo(world, grid, K):
+    """The 2-D grid sharding with collectives in place of the fused epilogues (same tiles, same ownership, same operand
+    layout): all-gather of every hop output inside the column group, all-to-all of the slices inside the row group.
+    Forward and backward (dh, dx tiles, db) against the sparse oracle; G = 8 features split over the column groups."""
+    err = _run("gloo", "grid", "float64", world=world, G=8, grid=grid, K=K)
     assert err < 1e-12, err
 
 
