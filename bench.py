@@ -281,8 +281,16 @@ def cpu_baseline_block(w, reps):
     threads = usable_cores()
     n_dense = pick_dense_n(w)
     ops_s, t, nnz_d, ts = cpu_dense_sample(w, n_dense, reps, threads)
+    # the dense algorithm does O(N^2) work for O(N) non-zeros: its op/s falls like 1/N.  Measured at smaller N too
+    # ("report the measured 1/N trend rather than extrapolating silently"); cheap next to the sample above.
+    trend = []
+    for n_small in (1682, 4096, 8192):
+        if n_small < n_dense:
+            o_, t_, z_, _ = cpu_dense_sample(w, n_small, min(3, reps), threads)
+            trend.append({"N": n_small, "nnz": z_, "s_per_forward": t_, "ops_per_s": o_})
+    trend.append({"N": n_dense, "nnz": nnz_d, "s_per_forward": t, "ops_per_s": ops_s})
     return ops_s, t, {"value": ops_s, "unit": "edge-feature-op/s", "cores": threads, "kind": "port",
-                      "threads_pinned": threads, "host_cpus_visible": os.cpu_count(),
+                      "threads_pinned": threads, "host_cpus_visible": os.cpu_count(), "dense_trend": trend,
                       "sample": "reference dense torch.matmul algorithm at N=%d (nnz=%d), same avgDeg/K/G/F/B; 1 warm-up, "
                                 "median of %d forwards (min %.2f s, median %.2f s, max %.2f s); the dense algorithm is "
                                 "O(N^2) and cannot hold N=%d" % (n_dense, nnz_d, len(ts), min(ts), t, max(ts), w["N"])}
