@@ -435,7 +435,13 @@ def load_ncu_traffic(workload, dtype):
         return None
 
 
-def hop_roofline(ctx, hop_ms, step_ms_total, nnz, rows, C, kernel, workload=None):
+def hop_compulsory_bytes(nnz, rows, C, es=4, src_rows=None):
+    """Cache-ideal bytes of one hop: 2*N*C*s + nnz*(4+s); a row shard reads all `src_rows` source rows
+    and writes its own `rows`."""
+    return (int(rows if src_rows is None else src_rows) + int(rows)) * int(C) * es + int(nnz) * (4 + es)
+
+
+def hop_roofline(ctx, hop_ms, step_ms_total, nnz, rows, C, kernel, workload=None, src_rows=None):
     if not hop_ms:
         return None
     hop_bytes = hop_algorithmic_bytes(nnz, rows, C, ctx.es)
@@ -448,6 +454,10 @@ def hop_roofline(ctx, hop_ms, step_ms_total, nnz, rows, C, kernel, workload=None
            "kernel_share_of_step": float(np.sum(hop_ms)) / step_ms_total}
     if traffic:
         out["dram_frac"] = traffic / (avg * 1e-3) / 1e9 / ctx.peak      # actual DRAM bytes / time / copy peak
+    # SURVEY.md §8d secondary bound: what a kernel with perfect L2 reuse would move (every source row read once, every
+    # result row written once, the indices and values once)
+    out["compulsory_bytes"] = hop_compulsory_bytes(nnz, rows, C, ctx.es, src_rows)
+    out["compulsory_frac"] = out["compulsory_bytes"] / (avg * 1e-3) / 1e9 / ctx.peak
     return out
 
 
@@ -824,7 +834,7 @@ def multi_gpu_arm(ctx, w, out_fd):
     rf = hop_roofline(ctx, hop_ms, ms * max(1, len(hop_ms) // max(hops, 1)), nnz_loc, rows_loc, c_loc,
                       "hop kernel, rank 0 shard: %d rows x %d columns, %d nnz%s" %
                       (rows_loc, c_loc, nnz_loc, " (fused all-gather epilogue)" if mode == "nodes" and part.fused else
-                       (" (all-gather + scatter epilogue)" if mode == "grid" else "")))
+                       (" (all-gather + scatter epilogue)" if mode == "grid" else "")), src_rows=N)
     out["roofline"] = rf
     out["e2e"] = {"value": ops_per_step / (ms_e2e * 1e-3), "unit": "edge-feature-op/s",
                   "h2d_bytes_per_step": xh.numel() * es * world, "d2h_bytes_per_step": yh.numel() * es * world,

@@ -39,3 +39,15 @@ def test_gather_model_bytes():
     assert abs(b / (32_000_000 * 64) - 4.25) < 0.02           # 4.25 bytes per edge-feature op
     assert bench.hop_algorithmic_bytes(10, 5, 3, 8) == 10 * 12 + 6 * 8 + 10 * 24 + 5 * 24
     assert bench.WORKLOADS["er1m"]["N"] == 1_000_000 and bench.WORKLOADS["cfg2"]["B"] == 32
+    # the roofline block of one hop kernel, from launch times (no GPU needed for the arithmetic)
+    import types
+    ctx = types.SimpleNamespace(es=4, peak=6566.7, peak_src="test", args=types.SimpleNamespace(dtype="f32"))
+    rf = bench.hop_roofline(ctx, [1.0, 1.1, 0.9], 5.0 * 1, 32_000_000, 1_000_000, 64, "k")
+    assert rf["bytes_per_launch"] == b and rf["launches_timed"] == 3 and abs(rf["ms_per_launch"] - 1.0) < 1e-12
+    assert abs(rf["achieved"] - b / 1e-3 / 1e9) < 1e-6 and abs(rf["frac"] - rf["achieved"] / 6566.7) < 1e-12
+    assert abs(rf["kernel_share_of_step"] - 0.6) < 1e-12 and rf["traffic"] is None and "dram_frac" not in rf
+    assert rf["compulsory_bytes"] == 2 * 1_000_000 * 64 * 4 + 32_000_000 * 8              # 0.77 GB at the headline
+    assert abs(rf["compulsory_frac"] - rf["compulsory_bytes"] / 1e-3 / 1e9 / 6566.7) < 1e-12
+    rf = bench.hop_roofline(ctx, [1.0], 2.0, 32_000_000, 1_000_000, 64, "k", workload="er1m")
+    assert rf["traffic"] == 6287089304 and abs(rf["dram_frac"] - 6287089304 / 1e-3 / 1e9 / 6566.7) < 1e-12
+    assert bench.hop_roofline(ctx, [], 1.0, 1, 1, 1, "k") is None
